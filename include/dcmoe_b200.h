@@ -1,0 +1,184 @@
+/*
+ * dcmoe_b200.h -- C ABI of the B200-native DCMoE layer forward (libdcmoe_b200.so).
+ *
+ * Drop-in boundary for ONE path of UniMoE-Audio: UniMoEAudioSparseMoeBlock.forward
+ * (reference utils/UniMoE_Audio_core.py:236-358).  The reference has no FFI of its own (it is
+ * pure PyTorch); each entry point below names the reference lines it replaces, and
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - `row_capacity` is the number of rows of the h / y buffers the caller allocated (from
+ *     dcmoe_query_sizes); pass the same value to every call of one forward.
+ *   - extern "C", plain device pointers + sizes, a cudaStream_t passed as void*.  No torch types.
+ *   - every function returns 0 on success, a negative dcmoe_status otherwise;
+ *     dcmoe_last_error() returns a thread-local description of the last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - dtype: DCMOE_F32 or DCMOE_BF16 is the activation/weight dtype D of the layer
+ *     (bf16 at inference, reference utils/UniMoE_Audio_mod.py:44).  Integer outputs keep the
+ *     reference's dtypes: dynamic_top_k int64, expert_mask int32 (core.py:259, :165).
+ *   - no function synchronises the stream or reads device data on the host: the whole layer is
+ *     launch-only (CUDA-graph capturable); data-dependent sizes (rows per expert, tile lists)
+ *     live in the device-side plan.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DCMOE_ERR_CUDA.
+ *
+ * Row space.  Rows handed to the expert FFNs live in one "row space" of `row_capacity` rows:
+ *     [0, T_pad)                     shared-expert rows, row t = token t          (T_pad = ceil128(T))
+ *     [T_pad, T_pad + sum_e ceil128(count_e))   routed rows, expert-major, ascending token id inside
+ *                                    an expert (the canonical stable permutation)
+ * x_packed holds the routed part only (row - T_pad); h / y hold the whole row space.
+ */
+#ifndef DCMOE_B200_H_
+#define DCMOE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCMOE_ABI_VERSION 1
+
+typedef enum dcmoe_dtype { DCMOE_F32 = 0, DCMOE_BF16 = 1 } dcmoe_dtype;
+
+typedef enum dcmoe_status {
+    DCMOE_OK = 0,
+    DCMOE_ERR_INVALID = -1,     /* bad argument / unsupported configuration        */
+    DCMOE_ERR_CUDA = -2,        /* CUDA runtime / launch failure, or no CUDA device */
+    DCMOE_ERR_UNSUPPORTED = -3  /* valid reference config this build does not implement */
+} dcmoe_status;
+
+/* Constructor contract: the fields UniMoEAudioSparseMoeBlock.__init__ reads from
+ * utils/config.json["text_config"] (core.py:204-234, :24, :42). */
+typedef struct dcmoe_config {
+    int32_t hidden_size;               /* 2048  */
+    int32_t n_real;                    /* mlp_dynamic_expert_num       8 */
+    int32_t n_null;                    /* mlp_dynamic_null_expert_num  1 */
+    int32_t n_fix;                     /* mlp_fixed_expert_num         2 */
+    int32_t dynamic_intermediate_size; /* 2752  */
+    int32_t shared_intermediate_size;  /* 1376  (n_fix * shared == dynamic is required) */
+    int32_t dtype;                     /* dcmoe_dtype */
+    int32_t reserved;                  /* keep the doubles 8-byte aligned; must be 0 */
+    double top_p;                      /* mlp_dynamic_top_p     0.7  (python float) */
+    double jitter_eps;                 /* router_jitter_noise   0.01 (python float) */
+} dcmoe_config;
+
+/* Sizes of the device-side plan / workspace for T local tokens and `row_capacity` FFN rows. */
+typedef struct dcmoe_sizes {
+    int64_t n_blocks;          /* router token blocks (DCMOE_ROUTER_BLOCK tokens each)          */
+    int64_t t_pad;             /* ceil128(T)                                                    */
+    int64_t max_mtiles;        /* upper bound on 128-row tiles in row space                     */
+    int64_t row_capacity;      /* rows of h / y  (worst case t_pad + n_real*T + 128*n_real)     */
+    int64_t plan_bytes;        /* bytes of the plan buffer (counts, offsets, tile table, aux)   */
+} dcmoe_sizes;
+
+#define DCMOE_ROUTER_BLOCK 16
+#define DCMOE_TILE_M 128
+
+/* Offsets (in bytes) of the fields inside the plan buffer; all int32 unless noted. */
+typedef struct dcmoe_plan_layout {
+    int64_t block_counts;   /* [n_blocks][n_dyn] int32   per-block selected-token counts (router)  */
+    int64_t block_probs;    /* [n_blocks][n_dyn] float   per-block sums of aux softmax (router)    */
+    int64_t block_offsets;  /* [n_blocks][n_real] int32  exclusive prefix over blocks (plan)       */
+    int64_t counts;         /* [n_real] int32            tokens per routed expert (core.py:455)    */
+    int64_t seg_base;       /* [n_real+1] int32          row-space start of each routed segment;   */
+                            /*                           [n_real] = end of used row space          */
+    int64_t n_mtiles;       /* [1] int32                 number of valid entries in mtiles         */
+    int64_t aux_loss;       /* [1] float                 audio_load_balancing_loss_func result     */
+    int64_t mtiles;         /* [max_mtiles] dcmoe_mtile                                          */
+    int64_t total;          /* == plan_bytes */
+} dcmoe_plan_layout;
+
+typedef struct dcmoe_mtile {
+    int32_t a_row;     /* GEMM-1 A row: in x (group == n_real) or in x_packed (routed)  */
+    int32_t out_row;   /* row-space row of this tile (h, y, scales)                     */
+    int32_t group;     /* weight group: 0..n_real-1 routed expert, n_real = shared pack */
+    int32_t rows;      /* valid rows in this tile (1..128)                              */
+} dcmoe_mtile;
+
+const char* dcmoe_last_error(void);
+int dcmoe_abi_version(void);
+
+/* Fill `sizes` / `layout` for T tokens.  row_capacity_hint <= 0 selects the worst case. Host only. */
+int dcmoe_query_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_hint, dcmoe_sizes* sizes,
+                      dcmoe_plan_layout* layout);
+
+/*
+ * Router.  Replaces core.py:251 (gate Linear), :255 -> :157-167 (Top-P count), :259-284 (mixer loop ->
+ * :94-154, normalise), :286-291 (padding mask, shared columns), :293-300 -> :361-389 (aux-loss partials),
+ * :331-332 -> :178-193 (global weights).
+ *   x            [T, H] D
+ *   w_gate       [n_dyn + n_fix, H] D        (gate.weight)
+ *   logits_in    [T, E] D or NULL.  When given, the gate projection is skipped and routing runs on
+ *                these logits ("bit-exact given identical router logits").
+ *   attn_mask    [T] int32 (0/1) or NULL      (padding_token_mask, model.py:241)
+ * outputs
+ *   logits_out   [T, E] D          full_router_logits
+ *   top_k        [T] int64         dynamic_top_k
+ *   expert_mask  [T, E] int32      shared columns = 1
+ *   global_weight[T, E] D
+ *   plan         block_counts / block_probs sections are written
+ */
+int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
+                 const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
+                 void* global_weight, void* plan, void* stream);
+
+/*
+ * Plan: exact integer histogram -> exclusive prefix sums -> segment bases, tile table, aux loss.
+ * Replaces core.py:455 (capacity = mask.sum(0).max(), here exact per-expert counts instead of a padded
+ * capacity) and finishes core.py:376-389 (means over tokens, deterministic order).
+ */
+int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* plan, void* stream);
+
+/*
+ * Permute (dispatch).  Replaces core.py:459-462 + utils/UniMoE_Audio_utils.py:436-485
+ * (compress_matrix x2 + the 0/1 "ce,cem->ecm" einsum): rows of x are gathered into the packed
+ * routed part of row space with 128-bit loads/stores.
+ *   x_packed     [row_capacity - t_pad, H] D
+ *   slot_of      [T, n_real] int32   row-space row of (token, expert) or -1          (combine side)
+ *   row_token    [row_capacity] int32 token id of each routed row (-1 for padding / shared rows hold t)
+ *   row_scale    [row_capacity, 2] float  weights folded into the FFN: routed row -> (gw[t,e], gw[t,e]);
+ *                shared row t -> (gw[t,n_dyn], gw[t,n_dyn+1])        (core.py:447, :348)
+ */
+int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T,
+                  int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* x_packed, int32_t* slot_of,
+                  int32_t* row_token, float* row_scale, void* stream);
+
+/*
+ * Expert FFNs (routed + shared) as two grouped GEMMs over row space.  Replaces core.py:475 ->
+ * :406-416, :48-49 (24 cuBLAS calls on padded [C, H] blocks) and core.py:344-349 -> :30-31 (shared
+ * experts; packed as weight group n_real because n_fix * I_s == I_d).
+ *   w13          [n_real+1, 2*I_d, H] D   gate/up rows interleaved in blocks of 64
+ *   w2           [n_real+1, H, I_d] D
+ *   h            [row_capacity, I_d] D    silu(gate) * up * row_scale   (scratch)
+ *   y            [row_capacity, H] D      already weighted expert outputs
+ *   impl         0 = tcgen05/TMEM/TMA grouped GEMM (bf16 only), 1 = CUDA-core fp32-accumulate GEMM
+ *                (the fp32 layer path; also usable with bf16 for cross-checking)
+ *   phase        0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
+ *                put CUDA events between the two launches
+ */
+int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
+                      int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,
+                      int impl, int phase, void* stream);
+
+/*
+ * Combine.  Replaces core.py:486-488 + utils/UniMoE_Audio_utils.py:488-523 (decompress_matrix + "se,sem->sm"
+ * einsum), core.py:338-353 (zeros + adds of routed and shared outputs): per token, a gather of the shared
+ * row and of its <= n_real routed rows, fp32 accumulate in fixed order (deterministic, no atomics).
+ *   out          [T, H] D
+ */
+int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out, void* stream);
+
+/*
+ * Weight packing (one-off, at load time): from the reference's separate gate_proj / up_proj / down_proj
+ * matrices (state-dict keys in SURVEY.md 8b) into the grouped layouts above.
+ *   group        0..n_real-1: routed expert;  n_real: shared pack, `part` = shared expert index
+ *   gate_proj, up_proj [I, H] D;  down_proj [H, I] D     with I = I_d (routed) or I_s (shared)
+ */
+int dcmoe_pack_expert(const void* gate_proj, const void* up_proj, const void* down_proj, int group, int part,
+                      const dcmoe_config* cfg, void* w13, void* w2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCMOE_B200_H_ */

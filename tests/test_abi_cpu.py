@@ -1,0 +1,98 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every symbol that
+include/dcmoe_b200.h declares, validates configurations, and refuses to compute without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from unimoe_audio_b200 import DCMoE, _lib, ops
+from unimoe_audio_b200.ops import LayerDims
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dcmoe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcmoe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert "dcmoe_router" in declared and "dcmoe_grouped_ffn" in declared and len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dcmoe_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert lib.dcmoe_abi_version() == 1
+
+
+def test_query_sizes_reference_config():
+    dims = LayerDims()
+    sz, lay = ops.query_sizes(dims, torch.bfloat16, 8 * 2048)
+    assert sz.n_blocks == 1024 and sz.t_pad == 16384
+    assert sz.row_capacity == 16384 + 8 * 16384 + 8 * 128
+    assert sz.max_mtiles == sz.row_capacity // 128
+    assert lay.total == sz.plan_bytes and lay.mtiles % 16 == 0
+    sz0, _ = ops.query_sizes(dims, torch.float32, 0)
+    assert sz0.n_blocks == 0 and sz0.t_pad == 0
+    sz1, _ = ops.query_sizes(dims, torch.float32, 1)
+    assert sz1.n_blocks == 1 and sz1.t_pad == 128
+
+
+@pytest.mark.parametrize("bad", [
+    dict(n_fix=3, shared_intermediate_size=1376),            # shared pack must equal the routed size
+    dict(hidden_size=2000),                                   # H % 256
+    dict(top_p=0.0),                                          # fixed top-k mode not implemented
+    dict(n_real=14, n_null=1, n_fix=2),                       # more than 16 router columns
+])
+def test_invalid_configs_are_rejected_with_a_message(bad):
+    dims = LayerDims(**bad)
+    with pytest.raises(_lib.DcmoeError) as ei:
+        ops.query_sizes(dims, torch.bfloat16, 128)
+    assert len(str(ei.value)) > 20
+
+
+def test_module_mirrors_reference_interface():
+    cfg = dict(hidden_size=2048, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
+               mlp_dynamic_top_k=0.0, mlp_fixed_expert_num=2, dynamic_intermediate_size=2752,
+               shared_intermediate_size=1376, router_jitter_noise=0.01, ep_size=1, token_drop=False)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    keys = set(m.state_dict().keys())
+    assert "gate.weight" in keys
+    assert "fixed_real_moe.1.down_proj.weight" in keys
+    assert "dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts.7.up_proj.weight" in keys
+    assert len(keys) == 1 + 2 * 3 + 8 * 3
+    assert m.num_experts == 11 and m.mlp_dynamic_expert_num == 9
+    assert m.dynamic_real_moe.deepspeed_moe.ep_group is None
+    with pytest.raises(NotImplementedError):
+        DCMoE(dict(cfg, token_drop=True))
+    with pytest.raises(NotImplementedError):
+        DCMoE(dict(cfg, mlp_dynamic_top_p=0))
+
+
+def test_no_cpu_fallback():
+    cfg = dict(hidden_size=256, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
+               mlp_dynamic_top_k=0.0, mlp_fixed_expert_num=2, dynamic_intermediate_size=128,
+               shared_intermediate_size=64, router_jitter_noise=0.01)
+    m = DCMoE(cfg).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 256), None, None)
+    if not torch.cuda.is_available():
+        lib = _lib.load()
+        c = m.dims.c_config(torch.float32)
+        rc = lib.dcmoe_combine(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, c, ctypes.c_void_p(16), None)
+        assert rc == -2 and b"no CPU fallback" in lib.dcmoe_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "unimoe_audio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "route_oracle" not in text.replace("oracle/route_oracle.c", ""), f

@@ -1,0 +1,226 @@
+// api.cu -- extern "C" entry points of libdcmoe_b200.so (declared in include/dcmoe_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dcmoe {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t err, const char* what) {
+    if (err == cudaSuccess) return DCMOE_OK;
+    set_error("%s: %s", what, cudaGetErrorString(err));
+    return DCMOE_ERR_CUDA;
+}
+
+int validate_config(const dcmoe_config* cfg) {
+    if (cfg == nullptr) {
+        set_error("config is NULL");
+        return DCMOE_ERR_INVALID;
+    }
+    const int n_dyn = cfg->n_real + cfg->n_null;
+    if (cfg->dtype != DCMOE_F32 && cfg->dtype != DCMOE_BF16) {
+        set_error("dtype must be DCMOE_F32 or DCMOE_BF16 (got %d)", cfg->dtype);
+        return DCMOE_ERR_INVALID;
+    }
+    if (cfg->n_real < 1 || cfg->n_null < 0 || n_dyn > kMaxDyn || n_dyn + cfg->n_fix > kMaxDyn) {
+        set_error("expert counts out of range: n_real=%d n_null=%d n_fix=%d (n_real+n_null+n_fix <= %d)", cfg->n_real,
+                  cfg->n_null, cfg->n_fix, kMaxDyn);
+        return DCMOE_ERR_INVALID;
+    }
+    if (cfg->n_fix < 1 || cfg->n_fix > 2 ||
+        cfg->n_fix * cfg->shared_intermediate_size != cfg->dynamic_intermediate_size) {
+        set_error("shared experts must pack into one routed-size group: n_fix (1 or 2) * shared_intermediate_size "
+                  "== dynamic_intermediate_size (got %d * %d vs %d)",
+                  cfg->n_fix, cfg->shared_intermediate_size, cfg->dynamic_intermediate_size);
+        return DCMOE_ERR_UNSUPPORTED;
+    }
+    if (cfg->hidden_size % 256 != 0 || cfg->dynamic_intermediate_size % 64 != 0 ||
+        cfg->shared_intermediate_size % 32 != 0) {
+        set_error("hidden_size %% 256, dynamic_intermediate_size %% 64 and shared_intermediate_size %% 32 must be 0 "
+                  "(got %d, %d, %d)",
+                  cfg->hidden_size, cfg->dynamic_intermediate_size, cfg->shared_intermediate_size);
+        return DCMOE_ERR_UNSUPPORTED;
+    }
+    if (!(cfg->top_p > 0.0)) {
+        set_error("mlp_dynamic_top_p == 0 (fixed top-k routing) is not supported; the reference config uses 0.7");
+        return DCMOE_ERR_UNSUPPORTED;
+    }
+    return DCMOE_OK;
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_hint, dcmoe_sizes* sz,
+                      dcmoe_plan_layout* l) {
+    const int n_dyn = cfg->n_real + cfg->n_null;
+    sz->n_blocks = ceil_div(T, kRouterBlock);
+    sz->t_pad = round_up(T, kTileM);
+    const int64_t worst = sz->t_pad + (int64_t)cfg->n_real * T + (int64_t)kTileM * cfg->n_real;
+    sz->row_capacity = row_capacity_hint > 0 ? row_capacity_hint : worst;
+    if (sz->row_capacity < sz->t_pad) {
+        set_error("row_capacity %lld smaller than the shared-expert rows %lld", (long long)sz->row_capacity,
+                  (long long)sz->t_pad);
+        return DCMOE_ERR_INVALID;
+    }
+    sz->max_mtiles = sz->row_capacity / kTileM;
+    int64_t off = 0;
+    l->block_counts = off; off = align_up(off + sz->n_blocks * n_dyn * 4, 16);
+    l->block_probs = off;  off = align_up(off + sz->n_blocks * n_dyn * 4, 16);
+    l->block_offsets = off; off = align_up(off + sz->n_blocks * cfg->n_real * 4, 16);
+    l->counts = off;       off = align_up(off + kMaxDyn * 4, 16);
+    l->seg_base = off;     off = align_up(off + (kMaxDyn + 1) * 4, 16);
+    l->n_mtiles = off;     off = align_up(off + 4, 16);
+    l->aux_loss = off;     off = align_up(off + 4, 16);
+    l->mtiles = off;       off = align_up(off + sz->max_mtiles * (int64_t)sizeof(dcmoe_mtile), 16);
+    l->total = off;
+    sz->plan_bytes = off;
+    return DCMOE_OK;
+}
+
+// launchers implemented in the other translation units
+int launch_router(const void*, const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, void*, int64_t*,
+                  int32_t*, void*, int32_t*, float*, cudaStream_t);
+int launch_plan(int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView, cudaStream_t);
+int launch_permute(const void*, const int32_t*, const void*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
+                   void*, int32_t*, int32_t*, float*, cudaStream_t);
+int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, void*, cudaStream_t);
+int launch_pack(const void*, const void*, const void*, int, int, const dcmoe_config*, void*, void*, cudaStream_t);
+int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
+                    const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
+int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
+                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
+
+static int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); libdcmoe_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return DCMOE_ERR_CUDA;
+    }
+    return DCMOE_OK;
+}
+
+}  // namespace dcmoe
+
+using namespace dcmoe;
+
+extern "C" {
+
+const char* dcmoe_last_error(void) { return g_err; }
+int dcmoe_abi_version(void) { return DCMOE_ABI_VERSION; }
+
+int dcmoe_query_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_hint, dcmoe_sizes* sizes,
+                      dcmoe_plan_layout* layout) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (T < 0 || sizes == nullptr || layout == nullptr) {
+        set_error("dcmoe_query_sizes: bad arguments (T=%lld)", (long long)T);
+        return DCMOE_ERR_INVALID;
+    }
+    return fill_sizes(cfg, T, row_capacity_hint, sizes, layout);
+}
+
+#define DCMOE_PROLOGUE(T_)                                                      \
+    int rc = validate_config(cfg);                                              \
+    if (rc) return rc;                                                          \
+    if ((T_) < 0) { set_error("negative token count"); return DCMOE_ERR_INVALID; } \
+    if ((rc = require_device())) return rc;
+
+int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
+                 const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight,
+                 void* plan, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && ((logits_in == nullptr && (x == nullptr || w_gate == nullptr)) || !logits_out || !top_k || !expert_mask ||
+                  !global_weight || !plan)) {
+        set_error("dcmoe_router: NULL pointer argument");
+        return DCMOE_ERR_INVALID;
+    }
+    dcmoe_sizes sz; dcmoe_plan_layout l;
+    if ((rc = fill_sizes(cfg, T, 0, &sz, &l))) return rc;
+    PlanView pv = plan_view(plan, l);
+    return launch_router(x, w_gate, logits_in, attn_mask, T, cfg, logits_out, top_k, expert_mask, global_weight,
+                         pv.block_counts, pv.block_probs, (cudaStream_t)stream);
+}
+
+// NOTE: the plan layout depends on (T, row_capacity); callers pass the same row_capacity to every call of a forward.
+static int plan_for(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv) {
+    dcmoe_plan_layout l;
+    int rc = fill_sizes(cfg, T, row_capacity, sz, &l);
+    if (rc) return rc;
+    *pv = plan_view(plan, l);
+    return DCMOE_OK;
+}
+
+int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* plan, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (!plan) { set_error("dcmoe_plan: NULL plan"); return DCMOE_ERR_INVALID; }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = plan_for(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
+    return launch_plan(T, cfg, sz, pv, (cudaStream_t)stream);
+}
+
+int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T, int64_t row_capacity,
+                  const dcmoe_config* cfg, const void* plan, void* x_packed, int32_t* slot_of, int32_t* row_token,
+                  float* row_scale, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!x || !expert_mask || !global_weight || !plan || !x_packed || !slot_of || !row_token || !row_scale)) {
+        set_error("dcmoe_permute: NULL pointer argument");
+        return DCMOE_ERR_INVALID;
+    }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
+    return launch_permute(x, expert_mask, global_weight, T, cfg, sz, pv, x_packed, slot_of, row_token, row_scale,
+                          (cudaStream_t)stream);
+}
+
+int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
+                      int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,
+                      int impl, int phase, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!x || !x_packed || !w13 || !w2 || !row_scale || !plan || !h || !y)) {
+        set_error("dcmoe_grouped_ffn: NULL pointer argument");
+        return DCMOE_ERR_INVALID;
+    }
+    if (phase < 0 || phase > 2) { set_error("dcmoe_grouped_ffn: phase must be 0, 1 or 2"); return DCMOE_ERR_INVALID; }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
+    if (impl == 0) return launch_ffn_tcgen05(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
+                                             phase, (cudaStream_t)stream);
+    if (impl == 1) {
+        if (sz.max_mtiles > 65535) { set_error("CUDA-core FFN: too many row tiles (%lld)", (long long)sz.max_mtiles); return DCMOE_ERR_INVALID; }
+        return launch_ffn_simt(x, x_packed, w13, w2, row_scale, T, cfg, sz, pv, h, y, phase, (cudaStream_t)stream);
+    }
+    set_error("dcmoe_grouped_ffn: unknown impl %d", impl);
+    return DCMOE_ERR_INVALID;
+}
+
+int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!y || !slot_of || !out)) { set_error("dcmoe_combine: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    return launch_combine(y, slot_of, T, cfg, out, (cudaStream_t)stream);
+}
+
+int dcmoe_pack_expert(const void* gate_proj, const void* up_proj, const void* down_proj, int group, int part,
+                      const dcmoe_config* cfg, void* w13, void* w2, void* stream) {
+    DCMOE_PROLOGUE(0)
+    if (!gate_proj || !up_proj || !down_proj || !w13 || !w2) { set_error("dcmoe_pack_expert: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    if (group < 0 || group > cfg->n_real || part < 0 || (group == cfg->n_real ? part >= cfg->n_fix : part != 0)) {
+        set_error("dcmoe_pack_expert: bad group/part (%d, %d)", group, part);
+        return DCMOE_ERR_INVALID;
+    }
+    return launch_pack(gate_proj, up_proj, down_proj, group, part, cfg, w13, w2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// ffn_simt.cu -- CUDA-core grouped expert FFN with fp32 accumulation.
+//
+// This is the fp32 layer path (north_star: outputs within rtol 1e-5 in fp32 -- tensor cores have no
+// fp32 x fp32 mode, so fp32 runs on FFMA) and an independent cross-check of the tcgen05 kernels in
+// bf16.  It is NOT the bf16 hot path (that is ffn_tcgen05.cu).  Same data layout, same plan, same
+// epilogue maths: GEMM-1 computes h = silu(x Wg^T) * (x Wu^T) * row_scale, GEMM-2 y = h W2^T
+// (reference core.py:48-49, :30-31, :447, :348).
+#include "common.cuh"
+
+namespace dcmoe {
+namespace {
+
+template <bool BF16>
+__device__ __forceinline__ float load_elem(const void* p, int64_t i) {
+    if (BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+    return static_cast<const float*>(p)[i];
+}
+template <bool BF16>
+__device__ __forceinline__ void store_elem(void* p, int64_t i, float v) {
+    if (BF16)
+        static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+    else
+        static_cast<float*>(p)[i] = v;
+}
+
+// CTA: 128 rows (one m-tile) x 64 output columns, 256 threads, thread = 8 rows x 4 cols.
+// SWIGLU: B holds 64 gate rows then 64 up rows per 64-column block (the W13 interleave).
+template <bool BF16, bool SWIGLU>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const void* __restrict__ a_shared_src,  // x (GEMM-1 shared group)
+                                                        const void* __restrict__ a_main,        // x_packed or h
+                                                        const void* __restrict__ w, const float* __restrict__ row_scale,
+                                                        int K, int N_out, int n_real, int I_s, int t_pad,
+                                                        const dcmoe_mtile* __restrict__ mtiles,
+                                                        const int32_t* __restrict__ n_mtiles, void* __restrict__ out) {
+    constexpr int BM = 128, BN = 64, BK = 16;
+    constexpr int NB = SWIGLU ? 2 : 1;
+    const int mt_idx = blockIdx.y;
+    if (mt_idx >= *n_mtiles) return;
+    const dcmoe_mtile mt = mtiles[mt_idx];
+    const int n0 = blockIdx.x * BN;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[NB][BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tr = (tid / 16) * 8, tc = (tid % 16) * 4;
+
+    const void* a_base;
+    int64_t a_row0;
+    if (SWIGLU) {  // GEMM-1: A = x rows (shared group) or x_packed rows
+        if (mt.group == n_real) { a_base = a_shared_src; a_row0 = mt.a_row; }
+        else { a_base = a_main; a_row0 = mt.a_row; }
+    } else {       // GEMM-2: A = h rows in row space
+        a_base = a_main; a_row0 = mt.out_row;
+    }
+    // weight rows of this CTA
+    const int64_t w_rows_per_group = SWIGLU ? 2 * (int64_t)N_out : (int64_t)N_out;
+    const int64_t wb0 = (int64_t)mt.group * w_rows_per_group + (SWIGLU ? (int64_t)(n0 / 64) * 128 : n0);
+
+    float acc[NB][8][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[b][i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += 256) {
+            const int r = i / BK, kk = i % BK;
+            As[kk][r] = (r < mt.rows) ? load_elem<BF16>(a_base, (a_row0 + r) * (int64_t)K + k0 + kk) : 0.f;
+        }
+        for (int i = tid; i < NB * BN * BK; i += 256) {
+            const int b = i / (BN * BK), rem = i % (BN * BK);
+            const int n = rem / BK, kk = rem % BK;
+            const bool ok = n0 + n < N_out;
+            Bs[b][kk][n] = ok ? load_elem<BF16>(w, (wb0 + b * 64 + n) * (int64_t)K + k0 + kk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float av[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = As[kk][tr + i];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float bv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = Bs[b][kk][tc + j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[b][i][j] = fmaf(av[i], bv[j], acc[b][i][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = tr + i;
+        if (r >= mt.rows) continue;
+        const int64_t orow = (int64_t)mt.out_row + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tc + j;
+            if (n >= N_out) continue;
+            float v;
+            if (SWIGLU) {
+                const float g = acc[0][i][j], u = acc[1][i][j];
+                const float sc = (mt.group == n_real && n >= I_s) ? row_scale[2 * orow + 1] : row_scale[2 * orow];
+                v = (g / (1.0f + expf(-g))) * u * sc;
+            } else {
+                v = acc[0][i][j];
+            }
+            store_elem<BF16>(out, orow * (int64_t)N_out + n, v);
+        }
+    }
+}
+
+}  // namespace
+
+int launch_ffn_simt(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
+                    int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv, void* h, void* y,
+                    int phase, cudaStream_t stream) {
+    if (T == 0) return DCMOE_OK;
+    const int H = cfg->hidden_size, Id = cfg->dynamic_intermediate_size;
+    dim3 block(256);
+    dim3 g1((unsigned)ceil_div(Id, 64), (unsigned)sz.max_mtiles), g2((unsigned)ceil_div(H, 64), (unsigned)sz.max_mtiles);
+    if (cfg->dtype == DCMOE_BF16) {
+        if (phase != 2) simt_gemm_kernel<true, true><<<g1, block, 0, stream>>>(x, x_packed, w13, row_scale, H, Id, cfg->n_real,
+                                                               cfg->shared_intermediate_size, (int)sz.t_pad, pv.mtiles,
+                                                               pv.n_mtiles, h);
+        if (phase != 1) simt_gemm_kernel<true, false><<<g2, block, 0, stream>>>(nullptr, h, w2, row_scale, Id, H, cfg->n_real,
+                                                                cfg->shared_intermediate_size, (int)sz.t_pad, pv.mtiles,
+                                                                pv.n_mtiles, y);
+    } else {
+        if (phase != 2) simt_gemm_kernel<false, true><<<g1, block, 0, stream>>>(x, x_packed, w13, row_scale, H, Id, cfg->n_real,
+                                                                cfg->shared_intermediate_size, (int)sz.t_pad, pv.mtiles,
+                                                                pv.n_mtiles, h);
+        if (phase != 1) simt_gemm_kernel<false, false><<<g2, block, 0, stream>>>(nullptr, h, w2, row_scale, Id, H, cfg->n_real,
+                                                                 cfg->shared_intermediate_size, (int)sz.t_pad, pv.mtiles,
+                                                                 pv.n_mtiles, y);
+    }
+    return check_cuda(cudaGetLastError(), "simt_gemm_kernel launch");
+}
+
+}  // namespace dcmoe

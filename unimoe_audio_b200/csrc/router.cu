@@ -1,0 +1,373 @@
+// router.cu -- fused gate projection + Top-P router for the DCMoE layer (sm_100a).
+//
+// Replaces (reference utils/UniMoE_Audio_core.py):
+//   :251        gate Linear            x[T,H] @ W_g^T -> logits[T,E]
+//   :157-167    audio_dynamic_expert_selection   (softmax -> sort -> cumsum -> >= p -> count)
+//   :262-282    the Python loop over top_k groups + audio_sparse_expert_mixer (:94-154, eval branch)
+//   :284        normalisation, :286-291 padding mask / shared columns
+//   :361-389    aux-loss per-token terms (block partial sums; finished in plan.cu)
+//   :178-193    calculate_audio_global_routing_weight
+//
+// One CTA (4 warps) owns DCMOE_ROUTER_BLOCK = 16 tokens.
+//   phase 1 (bf16): the skinny GEMM [16, H] x [H, 16] runs on mma.sync.m16n8k16 with the K
+//     dimension split across the 4 warps.  x is streamed straight from HBM with 128-bit loads
+//     (each row is read exactly once, full 32 B sectors); W_g (45 KB) stays L1/L2 resident.
+//     The K order inside a 16-element MMA step is permuted identically for A and B so that each
+//     lane's 16 B load feeds two MMA steps without any shuffle.  fp32 accumulators.
+//     A CUDA-core FFMA version of this product needs 22.5 kFMA/token, i.e. about as long as the
+//     HBM read of x itself; the tensor-core form makes the kernel purely HBM bound.
+//   phase 1 (fp32): FFMA dot products (parity path, not a performance target).
+//   phase 2: half-warp per token.  Lane j holds logit j; softmax / rank-sort / running sum /
+//     arg-max with lowest-index tie-break are built from __shfl_sync / __ballot_sync.  All
+//     floating point follows the canonical arithmetic of oracle/route_oracle.c (explicit
+//     __f*_rn intrinsics, never contracted), so dynamic_top_k, expert_mask AND global_weight
+//     are bit-identical to the oracle for identical logits.
+#include "common.cuh"
+
+namespace dcmoe {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float pow2if(int q) { return __int_as_float((q + 127) << 23); }
+
+// Sleef_expf_u10 restated with single-rounding intrinsics (see oracle/route_oracle.c)
+__device__ __forceinline__ float exp_sleef_u10(float d) {
+    float qf = rintf(__fmul_rn(d, 1.442695040888963407359924681001892137426645954152985934135449406931f));
+    int q = (int)qf;
+    float s = __fmaf_rn(qf, -0.693145751953125f, d);
+    s = __fmaf_rn(qf, -1.428606765330187045e-06f, s);
+    float u = 0.000198527617612853646278381f;
+    u = __fmaf_rn(u, s, 0.00139304355252534151077271f);
+    u = __fmaf_rn(u, s, 0.00833336077630519866943359f);
+    u = __fmaf_rn(u, s, 0.0416664853692054748535156f);
+    u = __fmaf_rn(u, s, 0.166666671633720397949219f);
+    u = __fmaf_rn(u, s, 0.5f);
+    u = __fadd_rn(1.0f, __fmaf_rn(__fmul_rn(s, s), u, s));
+    u = __fmul_rn(__fmul_rn(u, pow2if(q >> 1)), pow2if(q - (q >> 1)));
+    if (d < -104.0f) u = 0.0f;
+    if (d > 100.0f) u = __int_as_float(0x7f800000);
+    return u;
+}
+
+// correctly rounded expf via the double-precision exp (bf16 path of ATen's softmax uses std::exp)
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+
+template <bool BF16>
+__device__ __forceinline__ float rnd(float v) {
+    return BF16 ? bf16_round(v) : v;
+}
+
+// softmax over lanes [0, n) of a 16-lane group; lanes >= n must hold -inf.  Sequential sum in
+// lane order, multiply by the reciprocal, round to D -- the ATen CPU order.
+template <bool BF16>
+__device__ __forceinline__ float softmax_lanes(float v, int j, int n) {
+    float m = v;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, off, 16));
+    float e = 0.0f;
+    if (j < n) e = BF16 ? exp_cr(__fsub_rn(v, m)) : exp_sleef_u10(__fsub_rn(v, m));
+    float s = __shfl_sync(kFull, e, 0, 16);
+#pragma unroll
+    for (int i = 1; i < kMaxDyn; ++i) {
+        float ei = __shfl_sync(kFull, e, i, 16);
+        if (i < n) s = __fadd_rn(s, ei);
+    }
+    float inv = __fdiv_rn(1.0f, s);
+    return rnd<BF16>(__fmul_rn(e, inv));
+}
+
+// torch.sum over an inner dim of length n <= 16: ATen row_sum with 8 interleaved partial sums
+__device__ __forceinline__ float row_sum8_lanes(float d, int n) {
+    const int n8 = n >> 3;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        acc[k] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float v = __shfl_sync(kFull, d, 8 * i + k, 16);
+            if (i < n8) acc[k] = __fadd_rn(acc[k], v);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxDyn; ++i) {
+        float v = __shfl_sync(kFull, d, i, 16);
+        if (i >= 8 * n8 && i < n) acc[0] = __fadd_rn(acc[0], v);
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc[0] = __fadd_rn(acc[0], acc[k]);
+    return acc[0];
+}
+
+struct RouteConsts {
+    float thr_p, thr_eps, plus_eps, finfo_min;
+    int n_dyn, E;
+};
+
+// Route one token per 16-lane group.  l = logit of lane j (D-representable fp32), am = padding mask.
+template <bool BF16>
+__device__ __forceinline__ void route_token(float l, int j, int half, int am, const RouteConsts& rc, int& raw_out,
+                                            int& mask_out, float& gw_out, float& ga_out) {
+    const int n_dyn = rc.n_dyn, E = rc.E;
+    const float ninf = __int_as_float(0xff800000);
+    const bool dyn = j < n_dyn;
+    // ---- Top-P count (core.py:162-166) ----
+    float p = softmax_lanes<BF16>(dyn ? l : ninf, j, n_dyn);
+    int rank = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxDyn; ++i) {
+        float pi = __shfl_sync(kFull, p, i, 16);
+        if (i < n_dyn) rank += (pi > p) || (pi == p && i < j);
+    }
+    int raw = 1;
+    float run = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kMaxDyn; ++r) {
+        unsigned b = __ballot_sync(kFull, dyn && rank == r);
+        b = (b >> (half * 16)) & 0xffffu;
+        int src = __ffs(b) - 1;
+        float val = __shfl_sync(kFull, p, src & 15, 16);
+        if (r < n_dyn) {
+            run = __fadd_rn(run, val);
+            float c = rnd<BF16>(run);
+            raw += !(c >= rc.thr_p);
+        }
+    }
+    raw_out = raw;
+    const int k = raw <= n_dyn ? raw : 0;
+    int kmax = max(k, __shfl_xor_sync(kFull, k, 16));
+    // ---- mixer (core.py:103-147, eval branch) ----
+    float rem = dyn ? l : ninf;
+    float rw = 0.0f;
+    int sel = 0;
+    for (int it = 0; it < kmax; ++it) {
+        float bv = rem;
+        int bi = j;
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+            float ov = __shfl_xor_sync(kFull, bv, off, 16);
+            int oi = __shfl_xor_sync(kFull, bi, off, 16);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        const float thr = bv;
+        const float fac = fmaxf(fabsf(l), fabsf(thr));
+        const float diff = rnd<BF16>(__fsub_rn(thr, l));
+        const float ratio = rnd<BF16>(__fdiv_rn(diff, fac));
+        const bool drop = ratio > rc.thr_eps;
+        const float g = (dyn && !drop) ? rem : ninf;
+        const float sm = softmax_lanes<BF16>(g, j, n_dyn);
+        if (it < k && j == bi) {
+            rw = sm;
+            sel = 1;
+            rem = ninf;
+        }
+    }
+    // ---- normalise (core.py:284) ----
+    const float rs = rnd<BF16>(row_sum8_lanes(dyn ? rw : 0.0f, n_dyn));
+    const float den = rnd<BF16>(__fadd_rn(rs, rc.plus_eps));
+    rw = rnd<BF16>(__fdiv_rn(rw, den));
+    // ---- padding mask, shared experts always on (core.py:286-291) ----
+    int mk = dyn ? sel * am : (j < E ? 1 : 0);
+    // ---- aux-loss softmax (core.py:370-373) ----
+    ga_out = softmax_lanes<BF16>(dyn ? (mk ? l : rc.finfo_min) : ninf, j, n_dyn);
+    // ---- global weights (core.py:188-192) ----
+    const float G = softmax_lanes<BF16>((j < E && mk) ? l : ninf, j, E);
+    const float dsum = rnd<BF16>(row_sum8_lanes(dyn ? G : 0.0f, n_dyn));
+    gw_out = dyn ? rnd<BF16>(__fmul_rn(rw, dsum)) : G;
+    mask_out = mk;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_, const void* __restrict__ wg_,
+                                                     const void* __restrict__ logits_in_,
+                                                     const int32_t* __restrict__ attn_mask, int64_t T, int H,
+                                                     RouteConsts rc, void* __restrict__ logits_out_,
+                                                     int64_t* __restrict__ top_k, int32_t* __restrict__ expert_mask,
+                                                     void* __restrict__ gw_out_, int32_t* __restrict__ block_counts,
+                                                     float* __restrict__ block_probs) {
+    using elem_t = typename std::conditional<BF16, __nv_bfloat16, float>::type;
+    __shared__ float red[4][kRouterBlock][16];
+    __shared__ int s_cnt[kRouterBlock][kMaxDyn];
+    __shared__ float s_prob[kRouterBlock][kMaxDyn];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t tok0 = (int64_t)blockIdx.x * kRouterBlock;
+    const int E = rc.E;
+
+    if (logits_in_ == nullptr) {
+        const int Kq = H >> 2;  // columns per warp
+        const int k0 = warp * Kq;
+        if constexpr (BF16) {
+            const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_);
+            const __nv_bfloat16* wg = static_cast<const __nv_bfloat16*>(wg_);
+            const int g = lane >> 2, tq = lane & 3;
+            const int64_t r0 = tok0 + g, r1 = r0 + 8;
+            const bool v0 = r0 < T, v1 = r1 < T;
+            const __nv_bfloat16* xr0 = x + (v0 ? r0 : 0) * (int64_t)H + k0 + tq * 8;
+            const __nv_bfloat16* xr1 = x + (v1 ? r1 : 0) * (int64_t)H + k0 + tq * 8;
+            const bool wv0 = g < E, wv1 = g + 8 < E;
+            const __nv_bfloat16* w0 = wg + (int64_t)(wv0 ? g : 0) * H + k0 + tq * 8;
+            const __nv_bfloat16* w1 = wg + (int64_t)(wv1 ? g + 8 : 0) * H + k0 + tq * 8;
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            const int steps = Kq >> 5;  // 32-column steps
+            for (int s0 = 0; s0 < steps; s0 += 4) {
+                uint4 a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {  // batch the HBM loads: 8 x 16 B in flight per lane
+                    a[u] = v0 ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;
+                    b[u] = v1 ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 q0 = wv0 ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
+                    uint4 q1 = wv1 ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
+                    mma_bf16_16816(c0, a[u].x, b[u].x, a[u].y, b[u].y, q0.x, q0.y);
+                    mma_bf16_16816(c0, a[u].z, b[u].z, a[u].w, b[u].w, q0.z, q0.w);
+                    mma_bf16_16816(c1, a[u].x, b[u].x, a[u].y, b[u].y, q1.x, q1.y);
+                    mma_bf16_16816(c1, a[u].z, b[u].z, a[u].w, b[u].w, q1.z, q1.w);
+                }
+            }
+            red[warp][g][2 * tq] = c0[0];
+            red[warp][g][2 * tq + 1] = c0[1];
+            red[warp][g + 8][2 * tq] = c0[2];
+            red[warp][g + 8][2 * tq + 1] = c0[3];
+            red[warp][g][8 + 2 * tq] = c1[0];
+            red[warp][g][8 + 2 * tq + 1] = c1[1];
+            red[warp][g + 8][8 + 2 * tq] = c1[2];
+            red[warp][g + 8][8 + 2 * tq + 1] = c1[3];
+        } else {
+            // fp32 parity path: FFMA dot products, 2 tokens at a time, warp-reduced
+            const float* x = static_cast<const float*>(x_);
+            const float* wg = static_cast<const float*>(wg_);
+            for (int r = 0; r < kRouterBlock; r += 2) {
+                const int64_t ra = tok0 + r, rb = ra + 1;
+                const bool va = ra < T, vb = rb < T;
+                float acc_a[kMaxDyn], acc_b[kMaxDyn];
+#pragma unroll
+                for (int e = 0; e < kMaxDyn; ++e) acc_a[e] = acc_b[e] = 0.f;
+                for (int c = lane * 4; c < Kq; c += 128) {
+                    float4 xa = va ? *reinterpret_cast<const float4*>(x + ra * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
+                    float4 xb = vb ? *reinterpret_cast<const float4*>(x + rb * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
+#pragma unroll
+                    for (int e = 0; e < kMaxDyn; ++e) {
+                        if (e < E) {
+                            float4 w = *reinterpret_cast<const float4*>(wg + (int64_t)e * H + k0 + c);
+                            acc_a[e] += xa.x * w.x + xa.y * w.y + xa.z * w.z + xa.w * w.w;
+                            acc_b[e] += xb.x * w.x + xb.y * w.y + xb.z * w.z + xb.w * w.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < kMaxDyn; ++e) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        acc_a[e] += __shfl_xor_sync(kFull, acc_a[e], off);
+                        acc_b[e] += __shfl_xor_sync(kFull, acc_b[e], off);
+                    }
+                    if (lane == 0) {
+                        red[warp][r][e] = acc_a[e];
+                        red[warp][r + 1][e] = acc_b[e];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: half-warp per token ----
+    const int half = lane >> 4, j = lane & 15;
+    const elem_t* logits_in = static_cast<const elem_t*>(logits_in_);
+    elem_t* logits_out = static_cast<elem_t*>(logits_out_);
+    elem_t* gw_out = static_cast<elem_t*>(gw_out_);
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int tl = warp * 4 + round * 2 + half;  // token within block
+        const int64_t t = tok0 + tl;
+        const bool valid = t < T;
+        float l = 0.0f;
+        if (j < E) {
+            if (logits_in != nullptr) {
+                if (valid) l = BF16 ? __bfloat162float(((const __nv_bfloat16*)logits_in)[t * E + j])
+                                    : ((const float*)logits_in)[t * E + j];
+            } else {
+                l = __fadd_rn(__fadd_rn(__fadd_rn(red[0][tl][j], red[1][tl][j]), red[2][tl][j]), red[3][tl][j]);
+                l = rnd<BF16>(l);
+            }
+        }
+        const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
+        int raw, mk;
+        float gw, ga;
+        route_token<BF16>(l, j, half, am, rc, raw, mk, gw, ga);
+        if (valid && j < E) {
+            if constexpr (BF16) {
+                ((__nv_bfloat16*)logits_out)[t * E + j] = __float2bfloat16_rn(l);
+                ((__nv_bfloat16*)gw_out)[t * E + j] = __float2bfloat16_rn(gw);
+            } else {
+                ((float*)logits_out)[t * E + j] = l;
+                ((float*)gw_out)[t * E + j] = gw;
+            }
+            expert_mask[t * E + j] = mk;
+            if (j == 0) top_k[t] = raw;
+        }
+        s_cnt[tl][j] = (valid && j < rc.n_dyn) ? mk : 0;
+        s_prob[tl][j] = (valid && j < rc.n_dyn) ? ga : 0.0f;
+    }
+    __syncthreads();
+    if (tid < rc.n_dyn) {  // fixed-order block partials -> deterministic aux loss and exact counts
+        int cnt = 0;
+        float pr = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kRouterBlock; ++r) {
+            cnt += s_cnt[r][tid];
+            pr = __fadd_rn(pr, s_prob[r][tid]);
+        }
+        block_counts[(int64_t)blockIdx.x * rc.n_dyn + tid] = cnt;
+        block_probs[(int64_t)blockIdx.x * rc.n_dyn + tid] = pr;
+    }
+}
+
+}  // namespace
+
+int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
+                  const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
+                  void* global_weight, int32_t* block_counts, float* block_probs, cudaStream_t stream) {
+    if (T == 0) return DCMOE_OK;
+    const bool bf16 = cfg->dtype == DCMOE_BF16;
+    RouteConsts rc;
+    rc.n_dyn = cfg->n_real + cfg->n_null;
+    rc.E = rc.n_dyn + cfg->n_fix;
+    // scalar operands are rounded to D exactly as torch does for a wrapped python scalar
+    auto r = [&](float v) { return bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : v; };
+    rc.thr_p = r((float)cfg->top_p);
+    rc.thr_eps = r((float)(2.0 * cfg->jitter_eps));
+    rc.plus_eps = r(1e-6f);
+    rc.finfo_min = bf16 ? -3.3895313892515355e38f : -3.4028234663852886e38f;
+    const int64_t n_blocks = ceil_div(T, kRouterBlock);
+    dim3 grid((unsigned)n_blocks), block(128);
+    if (bf16) {
+        router_kernel<true><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc,
+                                                        logits_out, top_k, expert_mask, global_weight, block_counts,
+                                                        block_probs);
+    } else {
+        router_kernel<false><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc,
+                                                         logits_out, top_k, expert_mask, global_weight, block_counts,
+                                                         block_probs);
+    }
+    return check_cuda(cudaGetLastError(), "router_kernel launch");
+}
+
+}  // namespace dcmoe

@@ -1,0 +1,257 @@
+"""Drop-in DCMoE layer: the reference's ``UniMoEAudioSparseMoeBlock`` on hand-written sm_100a CUDA.
+
+Mirrors reference utils/UniMoE_Audio_core.py:196-358 at the boundary SURVEY.md section 8(b) describes:
+
+  * constructor: ``DCMoE(config)`` with ``config`` the (duck-typed) ``Qwen2_5_VLMoETextConfig`` built from
+    utils/config.json["text_config"]; the same attributes are read (core.py:204-234, :24, :42, :501);
+  * parameters / state-dict keys: ``gate.weight``, ``fixed_real_moe.{i}.{gate,up,down}_proj.weight``,
+    ``dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts.{e}.{gate,up,down}_proj.weight``
+    so ``from_pretrained`` / ``load_state_dict`` of real checkpoints work unchanged;
+  * call: ``forward(hidden_states, attention_mask, aux_balance_weight)`` -> the 6-tuple
+    ``(final_hidden_states, full_router_logits, dynamic_top_k, expert_mask, global_weight, aux_loss)``
+    with the reference's dtypes (x.dtype, x.dtype, int64, int32, x.dtype, float32 0-dim) (core.py:358).
+
+Swap-in (no edit to UniMoE_Audio_mod.py / UniMoE_Audio_model.py): either rebind
+``utils.UniMoE_Audio_model.UniMoEAudioSparseMoeBlock = DCMoE`` before the model is built, or after loading
+``for l in model.language_model.layers: l.mlp = DCMoE.from_reference(l.mlp)`` -- see INTEGRATION.md.
+
+The forward is launch-only (router -> plan -> permute -> grouped FFN -> combine, six kernels, no host
+synchronisation) and has NO CPU fallback: inputs must be CUDA tensors and the CUDA extension must load.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import LayerDims, Workspace
+
+
+def _cfg_get(config, name, default=None):
+    if isinstance(config, dict):
+        return config.get(name, default)
+    return getattr(config, name, default)
+
+
+class _ExpertMLP(nn.Module):
+    """Parameter holder with the reference's names (AudioSharedExpertMLP core.py:16-31 /
+    AudioDynamicExpertMLP core.py:34-49).  Compute happens in the grouped kernels, not here."""
+
+    def __init__(self, hidden_size: int, intermediate_size: int):
+        super().__init__()
+        self.hidden_size, self.intermediate_size = hidden_size, intermediate_size
+        self.gate_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
+        self.up_proj = nn.Linear(hidden_size, intermediate_size, bias=False)
+        self.down_proj = nn.Linear(intermediate_size, hidden_size, bias=False)
+
+    def forward(self, *_a, **_k):  # pragma: no cover - never used as a module
+        raise RuntimeError("expert MLPs are executed by the grouped sm_100a kernels, not individually")
+
+
+class _Experts(nn.Module):          # AudioExperts, core.py:392-416
+    def __init__(self, hidden_size, intermediate_size, num_local_experts):
+        super().__init__()
+        self.deepspeed_experts = nn.ModuleList([_ExpertMLP(hidden_size, intermediate_size) for _ in range(num_local_experts)])
+        self.num_local_experts = num_local_experts
+
+
+class _MOELayer(nn.Module):         # AudioMOELayer, core.py:419-493
+    def __init__(self, experts, ep_size, num_local_experts):
+        super().__init__()
+        self.experts = experts
+        self.ep_group = None
+        self.ep_size = ep_size
+        self.num_local_experts = num_local_experts
+
+    def _set_ep_group(self, ep_group):
+        self.ep_group = ep_group
+
+
+class _MoE(nn.Module):              # UniMoEAudioMoE, core.py:496-523
+    def __init__(self, hidden_size, intermediate_size, num_experts, ep_size):
+        super().__init__()
+        if num_experts % ep_size != 0:
+            raise ValueError(f"num_experts ({num_experts}) must be divisible by ep_size ({ep_size})")
+        self.ep_size = ep_size
+        self.num_experts = num_experts
+        self.num_local_experts = num_experts // ep_size
+        self.deepspeed_moe = _MOELayer(_Experts(hidden_size, intermediate_size, self.num_local_experts), ep_size,
+                                       self.num_local_experts)
+
+
+_WORKSPACES: Dict[tuple, Workspace] = {}
+
+
+def get_workspace(dims: LayerDims, dtype: torch.dtype, T: int, device, row_capacity: int = 0) -> Workspace:
+    """Workspaces are shared between layers (the 36 decoder layers run back to back on one stream)."""
+    key = (dims, dtype, T, torch.device(device), row_capacity)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        if len(_WORKSPACES) >= 4:
+            _WORKSPACES.pop(next(iter(_WORKSPACES)))
+        ws = Workspace(dims, dtype, T, device, row_capacity)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+class DCMoE(nn.Module):
+    """B200-native replacement of ``UniMoEAudioSparseMoeBlock`` (core.py:196)."""
+
+    def __init__(self, config, ffn_impl: Optional[int] = None):
+        super().__init__()
+        g = lambda n, d=None: _cfg_get(config, n, d)  # noqa: E731
+        # ---- the attributes the reference reads (core.py:204-234) ----
+        self.hidden_dim = g("hidden_size")
+        self.mlp_dynamic_real_expert_num = g("mlp_dynamic_expert_num")
+        self.mlp_dynamic_null_expert_num = g("mlp_dynamic_null_expert_num")
+        self.mlp_dynamic_expert_num = self.mlp_dynamic_real_expert_num + self.mlp_dynamic_null_expert_num
+        self.mlp_dynamic_top_p = g("mlp_dynamic_top_p")
+        self.mlp_dynamic_top_k = g("mlp_dynamic_top_k")
+        self.mlp_fixed_expert_num = g("mlp_fixed_expert_num")
+        self.num_experts = self.mlp_dynamic_expert_num + self.mlp_fixed_expert_num
+        self.ignore_differentiable_router = g("ignore_differentiable_router", True)
+        self.router_jitter_noise = g("router_jitter_noise")
+        self.input_jitter_noise = g("input_jitter_noise", 0.0)
+        self.min_capacity = g("min_capacity", 8)
+        self.capacity_factor = g("capacity_factor", 1.0)
+        self.token_drop = g("token_drop", False)
+        self.drop_policy = g("drop_policy", "probs")
+        self.avg_hidden_states_last = g("avg_hidden_states_last", False)
+        self.drop_token_num_print = g("drop_token_num_print", False)
+        self.fp32_gate = g("fp32_gate", False)
+        self.ep_size = g("ep_size", 1)
+        if self.mlp_dynamic_top_p == 0:
+            raise NotImplementedError("mlp_dynamic_top_p == 0 (fixed top-k routing, core.py:257) is not implemented; "
+                                      "the reference config uses top_p = 0.7")
+        if self.token_drop:
+            raise NotImplementedError("token_drop=True (core.py:302-329) is not implemented; utils/config.json sets it False")
+        if self.avg_hidden_states_last:
+            raise NotImplementedError("avg_hidden_states_last=True (core.py:355-356) is not implemented")
+        if g("hidden_act", "silu") != "silu":
+            raise NotImplementedError("only hidden_act='silu' (utils/config.json) is implemented")
+        self.dims = LayerDims(
+            hidden_size=self.hidden_dim, n_real=self.mlp_dynamic_real_expert_num, n_null=self.mlp_dynamic_null_expert_num,
+            n_fix=self.mlp_fixed_expert_num, dynamic_intermediate_size=g("dynamic_intermediate_size"),
+            shared_intermediate_size=g("shared_intermediate_size"), top_p=float(self.mlp_dynamic_top_p),
+            jitter_eps=float(self.router_jitter_noise))
+        # ---- parameters under the reference's names (core.py:220-222) ----
+        self.gate = nn.Linear(self.hidden_dim, self.num_experts, bias=False)
+        self.fixed_real_moe = nn.ModuleList(
+            [_ExpertMLP(self.hidden_dim, self.dims.shared_intermediate_size) for _ in range(self.mlp_fixed_expert_num)])
+        self.dynamic_real_moe = _MoE(self.hidden_dim, self.dims.dynamic_intermediate_size,
+                                     self.mlp_dynamic_real_expert_num, self.ep_size)
+        # ---- packed weights for the grouped kernels (built lazily from the parameters) ----
+        self._w13: Optional[torch.Tensor] = None
+        self._w2: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self.ffn_impl = ffn_impl          # None: tcgen05 for bf16, CUDA-core for fp32
+        self.row_capacity = 0             # 0 = worst case
+        self.last_workspace: Optional[Workspace] = None
+        self.stage_hook = None            # optional callable(stage_name) invoked between kernel launches (bench)
+
+    # ------------------------------------------------------------------ weights
+    @classmethod
+    def from_reference(cls, block: nn.Module, config=None, **kw) -> "DCMoE":
+        """Build from an instantiated reference block (or any module with the same state dict)."""
+        if config is None:
+            exp0 = block.dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts[0]
+            config = dict(
+                hidden_size=block.hidden_dim, mlp_dynamic_expert_num=block.mlp_dynamic_real_expert_num,
+                mlp_dynamic_null_expert_num=block.mlp_dynamic_null_expert_num, mlp_dynamic_top_p=block.mlp_dynamic_top_p,
+                mlp_dynamic_top_k=block.mlp_dynamic_top_k, mlp_fixed_expert_num=block.mlp_fixed_expert_num,
+                ignore_differentiable_router=block.ignore_differentiable_router,
+                router_jitter_noise=block.router_jitter_noise, input_jitter_noise=block.input_jitter_noise,
+                min_capacity=block.min_capacity, capacity_factor=block.capacity_factor, token_drop=block.token_drop,
+                drop_policy=block.drop_policy, avg_hidden_states_last=block.avg_hidden_states_last,
+                drop_token_num_print=block.drop_token_num_print, fp32_gate=block.fp32_gate,
+                ep_size=getattr(block.dynamic_real_moe, "ep_size", 1),
+                dynamic_intermediate_size=exp0.gate_proj.weight.shape[0],
+                shared_intermediate_size=block.fixed_real_moe[0].gate_proj.weight.shape[0], hidden_act="silu")
+        new = cls(config, **kw)
+        ref_param = next(block.parameters())
+        new.to(device=ref_param.device, dtype=ref_param.dtype)
+        new.load_state_dict(block.state_dict())
+        return new.eval()
+
+    def _expert_params(self):
+        routed = self.dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts
+        return routed, self.fixed_real_moe
+
+    def pack_weights(self, force: bool = False):
+        """(Re)build W13 [n_real+1, 2*I_d, H] (gate/up rows interleaved in blocks of 64) and
+        W2 [n_real+1, H, I_d]; group n_real is the shared-expert pack (2 x I_s = I_d)."""
+        p = self.gate.weight
+        routed, shared = self._expert_params()
+        key = (p.device, p.dtype, tuple(w._version for m in list(routed) + list(shared)
+                                        for w in (m.gate_proj.weight, m.up_proj.weight, m.down_proj.weight)))
+        if not force and self._w13 is not None and self._packed_key == key:
+            return
+        if not p.is_cuda:
+            raise RuntimeError("DCMoE needs its parameters on a CUDA device (no CPU fallback)")
+        d = self.dims
+        G = d.n_real + 1
+        w13 = torch.empty((G, 2 * d.dynamic_intermediate_size, d.hidden_size), dtype=p.dtype, device=p.device)
+        w2 = torch.empty((G, d.hidden_size, d.dynamic_intermediate_size), dtype=p.dtype, device=p.device)
+        for e, m in enumerate(routed):
+            ops.pack_expert(m.gate_proj.weight.detach().contiguous(), m.up_proj.weight.detach().contiguous(),
+                            m.down_proj.weight.detach().contiguous(), e, 0, d, w13, w2)
+        for i, m in enumerate(shared):
+            ops.pack_expert(m.gate_proj.weight.detach().contiguous(), m.up_proj.weight.detach().contiguous(),
+                            m.down_proj.weight.detach().contiguous(), d.n_real, i, d, w13, w2)
+        self._w13, self._w2, self._packed_key = w13, w2, key
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                aux_balance_weight: Optional[torch.Tensor] = None, router_logits: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        if self.training:
+            raise NotImplementedError("DCMoE implements the inference forward (eval mode); training-only branches "
+                                      "(fp32 gate, jitter, gumbel routing: core.py:240-249, :111-135) are out of scope")
+        if aux_balance_weight is not None:
+            raise NotImplementedError("aux_balance_weight (core.py:380-385) is training-only and not implemented")
+        if hidden_states.dim() != 3 or hidden_states.shape[-1] != self.hidden_dim:
+            raise ValueError(f"hidden_states must be [batch, seq, {self.hidden_dim}]")
+        if not hidden_states.is_cuda:
+            raise RuntimeError("DCMoE.forward needs CUDA tensors: there is no CPU fallback")
+        dt = hidden_states.dtype
+        if dt != self.gate.weight.dtype:
+            raise TypeError(f"hidden_states dtype {dt} != parameter dtype {self.gate.weight.dtype}")
+        if self.ep_size != 1:
+            raise NotImplementedError("ep_size > 1: use unimoe_audio_b200.ep.ExpertParallelDCMoE")
+        B, S, H = hidden_states.shape
+        T = B * S
+        x = hidden_states.reshape(T, H)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        self.pack_weights()
+        ws = get_workspace(self.dims, dt, T, x.device, self.row_capacity)
+        self.last_workspace = ws
+        wg = self.gate.weight.detach()
+        if not wg.is_contiguous():
+            wg = wg.contiguous()
+        hook = self.stage_hook or (lambda _name: None)
+        out = torch.empty((B, S, H), dtype=dt, device=x.device)
+        hook("start")
+        logits, top_k, mask, gw = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
+        hook("router")
+        ops.plan(ws)
+        hook("plan")
+        if T > 0:
+            ops.permute(x, mask, gw, ws)
+            hook("permute")
+            impl = self.ffn_impl if self.ffn_impl is not None else (0 if dt == torch.bfloat16 else 1)
+            ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
+            hook("ffn_gemm1")
+            ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)
+            hook("ffn_gemm2")
+            ops.combine(ws, out)
+            hook("combine")
+        aux = ws.aux_loss.clone().reshape(())
+        return out, logits, top_k, mask, gw, aux
+
+
+# The reference's class name, so `utils.UniMoE_Audio_model.UniMoEAudioSparseMoeBlock = ...` reads naturally.
+UniMoEAudioSparseMoeBlock = DCMoE

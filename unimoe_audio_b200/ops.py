@@ -1,0 +1,164 @@
+"""Thin torch-facing wrappers over the C ABI (device memory + streams only; no compute in Python).
+
+Each function mirrors one stage of ``UniMoEAudioSparseMoeBlock.forward`` (reference
+utils/UniMoE_Audio_core.py:236-358); see include/dcmoe_b200.h for the reference lines each replaces.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import DcmoeConfig, DcmoePlanLayout, DcmoeSizes
+
+_TORCH_DT = {torch.float32: _lib.DCMOE_F32, torch.bfloat16: _lib.DCMOE_BF16}
+
+
+@dataclass(frozen=True)
+class LayerDims:
+    hidden_size: int = 2048
+    n_real: int = 8
+    n_null: int = 1
+    n_fix: int = 2
+    dynamic_intermediate_size: int = 2752
+    shared_intermediate_size: int = 1376
+    top_p: float = 0.7
+    jitter_eps: float = 0.01
+
+    @property
+    def n_dyn(self) -> int:
+        return self.n_real + self.n_null
+
+    @property
+    def n_experts(self) -> int:
+        return self.n_dyn + self.n_fix
+
+    def c_config(self, dtype: torch.dtype) -> DcmoeConfig:
+        if dtype not in _TORCH_DT:
+            raise TypeError(f"DCMoE supports float32 and bfloat16, got {dtype}")
+        return DcmoeConfig(self.hidden_size, self.n_real, self.n_null, self.n_fix, self.dynamic_intermediate_size,
+                           self.shared_intermediate_size, _TORCH_DT[dtype], 0, float(self.top_p), float(self.jitter_eps))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def query_sizes(dims: LayerDims, dtype: torch.dtype, T: int, row_capacity: int = 0):
+    lib = _lib.load()
+    cfg = dims.c_config(dtype)
+    sz, lay = DcmoeSizes(), DcmoePlanLayout()
+    _lib.check(lib.dcmoe_query_sizes(cfg, T, row_capacity, sz, lay), "dcmoe_query_sizes")
+    return sz, lay
+
+
+class Workspace:
+    """Device buffers of one forward: the plan (counts / prefix sums / tile table / aux), the packed
+    rows, the FFN intermediates and the permutation maps.  Sized for the worst case (every token routed
+    to every real expert) unless ``row_capacity`` is given."""
+
+    def __init__(self, dims: LayerDims, dtype: torch.dtype, T: int, device, row_capacity: int = 0):
+        self.dims, self.dtype, self.T, self.device = dims, dtype, T, torch.device(device)
+        self.sizes, self.layout = query_sizes(dims, dtype, T, row_capacity)
+        self.row_capacity = int(self.sizes.row_capacity)
+        self.t_pad = int(self.sizes.t_pad)
+        dev = self.device
+        self.plan = torch.zeros(int(self.sizes.plan_bytes), dtype=torch.uint8, device=dev)
+        H, Id = dims.hidden_size, dims.dynamic_intermediate_size
+        self.x_packed = torch.empty((max(self.row_capacity - self.t_pad, 1), H), dtype=dtype, device=dev)
+        self.h = torch.empty((self.row_capacity, Id), dtype=dtype, device=dev)
+        self.y = torch.empty((self.row_capacity, H), dtype=dtype, device=dev)
+        self.slot_of = torch.empty((max(T, 1), dims.n_real), dtype=torch.int32, device=dev)
+        self.row_token = torch.full((self.row_capacity,), -1, dtype=torch.int32, device=dev)
+        self.row_scale = torch.zeros((self.row_capacity, 2), dtype=torch.float32, device=dev)
+
+    # typed views into the plan buffer (device tensors; reading them on the host synchronises)
+    def _view(self, off: int, n: int, dt: torch.dtype) -> torch.Tensor:
+        return self.plan[off: off + n * 4].view(dt)
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self._view(self.layout.counts, self.dims.n_real, torch.int32)
+
+    @property
+    def seg_base(self) -> torch.Tensor:
+        return self._view(self.layout.seg_base, self.dims.n_real + 1, torch.int32)
+
+    @property
+    def n_mtiles(self) -> torch.Tensor:
+        return self._view(self.layout.n_mtiles, 1, torch.int32)
+
+    @property
+    def aux_loss(self) -> torch.Tensor:
+        return self._view(self.layout.aux_loss, 1, torch.float32)
+
+    @property
+    def mtiles(self) -> torch.Tensor:
+        n = int(self.sizes.max_mtiles)
+        return self._view(self.layout.mtiles, n * 4, torch.int32).view(n, 4)
+
+
+def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Workspace, logits_in: Optional[torch.Tensor] = None,
+           attention_mask: Optional[torch.Tensor] = None):
+    """Top-P router.  Returns (full_router_logits, dynamic_top_k, expert_mask, global_weight)."""
+    lib = _lib.load()
+    dims, T, dt, dev = ws.dims, ws.T, ws.dtype, ws.device
+    E = dims.n_experts
+    logits = torch.empty((T, E), dtype=dt, device=dev)
+    top_k = torch.empty((T,), dtype=torch.int64, device=dev)
+    mask = torch.empty((T, E), dtype=torch.int32, device=dev)
+    gw = torch.empty((T, E), dtype=dt, device=dev)
+    am = None
+    if attention_mask is not None:
+        am = attention_mask.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+        if am.numel() != T:
+            raise ValueError("attention_mask must have one entry per token")
+    if logits_in is not None:
+        if logits_in.shape != (T, E) or logits_in.dtype != dt or not logits_in.is_contiguous():
+            raise ValueError("logits_in must be a contiguous [T, E] tensor of the layer dtype")
+    cfg = dims.c_config(dt)
+    _lib.check(lib.dcmoe_router(_ptr(x), _ptr(w_gate), _ptr(logits_in), _ptr(am), T, cfg, _ptr(logits), _ptr(top_k),
+                                _ptr(mask), _ptr(gw), _ptr(ws.plan), _stream()), "dcmoe_router")
+    return logits, top_k, mask, gw
+
+
+def plan(ws: Workspace):
+    lib = _lib.load()
+    _lib.check(lib.dcmoe_plan(ws.T, ws.row_capacity, ws.dims.c_config(ws.dtype), _ptr(ws.plan), _stream()), "dcmoe_plan")
+
+
+def permute(x: torch.Tensor, expert_mask: torch.Tensor, global_weight: torch.Tensor, ws: Workspace):
+    lib = _lib.load()
+    _lib.check(lib.dcmoe_permute(_ptr(x), _ptr(expert_mask), _ptr(global_weight), ws.T, ws.row_capacity,
+                                 ws.dims.c_config(ws.dtype), _ptr(ws.plan), _ptr(ws.x_packed), _ptr(ws.slot_of),
+                                 _ptr(ws.row_token), _ptr(ws.row_scale), _stream()), "dcmoe_permute")
+
+
+def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Workspace, impl: int = 0, phase: int = 0):
+    lib = _lib.load()
+    _lib.check(lib.dcmoe_grouped_ffn(_ptr(x), _ptr(ws.x_packed), _ptr(w13), _ptr(w2), _ptr(ws.row_scale), ws.T,
+                                     ws.row_capacity, ws.dims.c_config(ws.dtype), _ptr(ws.plan), _ptr(ws.h), _ptr(ws.y),
+                                     impl, phase, _stream()), "dcmoe_grouped_ffn")
+
+
+def combine(ws: Workspace, out: torch.Tensor):
+    lib = _lib.load()
+    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.dims.c_config(ws.dtype), _ptr(out), _stream()),
+               "dcmoe_combine")
+
+
+def pack_expert(gate_proj: torch.Tensor, up_proj: torch.Tensor, down_proj: torch.Tensor, group: int, part: int,
+                dims: LayerDims, w13: torch.Tensor, w2: torch.Tensor):
+    lib = _lib.load()
+    dt = w13.dtype
+    for t in (gate_proj, up_proj, down_proj):
+        if t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError("expert weights must be contiguous CUDA tensors of the packed dtype")
+    _lib.check(lib.dcmoe_pack_expert(_ptr(gate_proj), _ptr(up_proj), _ptr(down_proj), group, part, dims.c_config(dt),
+                                     _ptr(w13), _ptr(w2), _stream()), "dcmoe_pack_expert")
