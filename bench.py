@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- DCMoE layer forward throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward of one DCMoE layer (router -> plan -> permute -> grouped FFN -> combine) over one
+batch of synthetic activations.
+  N = 1 : BASELINE.json configs[1] -- batch 8 x 2048 tokens, bf16, utils/config.json dims.
+  N > 1 : BASELINE.json configs[3] -- expert-parallel, global batch 64 x 4096 tokens sharded by sequence,
+          8/N routed experts per rank, gate + shared experts replicated ("strong" scaling: the global batch
+          is fixed).
+Prints ONE JSON line (rank 0).  `value` = tokens/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = the same through the public module call with pinned HOST buffers (H2D of the step's input and D2H of
+the step's outputs inside the timed region); `roofline` describes the dominant kernel (GEMM-1 of the grouped
+FFN) from CUDA events recorded between the kernel launches of the timed steps; `cpu_baseline` is the oracle
+port (oracle/dcmoe_oracle.py) timed on this box's host cores on a bounded sample of the same workload.
+
+--impl reference times that same CPU restatement of the reference path (the reference itself is Python/PyTorch
+and /root/reference does not exist on the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dcmoe_layer_tokens_per_sec"
+UNIT = "tokens/s"
+KERNELS_PER_STEP = 6  # router, plan(+aux), permute, ffn gemm-1, ffn gemm-2, combine
+FLOP_PER_ROW_GEMM1 = 4 * 2048 * 2752  # gate + up projections
+FLOP_PER_ROW_GEMM2 = 2 * 2048 * 2752
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return dict(sm_mhz=statistics.median(load) if load else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_tokens_per_sec(sample_tokens: int, reps: int, warmup: int = 1):
+    """Time the CPU restatement of the reference path (oracle port) on all host cores."""
+    import torch
+
+    from oracle import dcmoe_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dt = torch.bfloat16
+    W = O.make_weights(seed=0, dtype=dt)
+    x = torch.randn(1, sample_tokens, 2048, generator=torch.Generator().manual_seed(1235)).to(dt)
+    for _ in range(warmup):
+        O.forward(x, W)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.forward(x, W)
+        times.append(time.perf_counter() - t0)
+    return sample_tokens / min(times), sample_tokens / (sum(times) / len(times)), cores, times
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sample = 2048
+    best, mean, cores, times = cpu_oracle_tokens_per_sec(sample, reps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    ms = 1e3 * sum(times) / len(times)
+    workload = ("configs[1]: single DCMoE layer bf16, batch 8 x 2048 tokens" if args.gpus == 1 else
+                "configs[3]: expert-parallel DCMoE, global batch 64 x 4096 tokens")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mean, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "note": "CPU oracle port of the reference path; each step = one forward over a "
+                                                 f"bounded sample of {sample} tokens of that workload"},
+        "cpu_baseline": {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"1 x {sample} tokens, bf16, all host threads, mean of {len(times)} steps"},
+        "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def build_module(dev, dt, ep_rank=0, ep_size=1):
+    import torch
+
+    from unimoe_audio_b200 import DCMoE
+
+    cfg = dict(hidden_size=2048, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
+               mlp_dynamic_top_k=0.0, mlp_fixed_expert_num=2, dynamic_intermediate_size=2752,
+               shared_intermediate_size=1376, router_jitter_noise=0.01, hidden_act="silu", ep_size=1)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    m = m.to(dt).to_empty(device=dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(0)
+    with torch.no_grad():
+        for _, p in sorted(m.named_parameters(), key=lambda kv: kv[0]):   # N(0, 0.02^2): initializer_range
+            p.copy_((torch.randn(p.shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt))
+    return m
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dt = torch.bfloat16
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    if world == 1:
+        B, S = 8, 2048
+        workload = "configs[1]: single DCMoE layer bf16 on 1xB200, batch 8 x 2048 tokens, utils/config.json dims"
+        m = build_module(dev, dt)
+        layer = m
+        scaling = "weak"
+        parallelism = "single GPU"
+    else:
+        from unimoe_audio_b200.ep import ExpertParallelDCMoE
+        Bg, S = 64, 4096
+        B = Bg // world
+        workload = (f"configs[3]: expert-parallel DCMoE across {world} B200, global batch 64 x 4096 tokens "
+                    f"({B} sequences and {8 // world} routed experts per rank)")
+        m = build_module(dev, dt)
+        layer = ExpertParallelDCMoE(m, dist.group.WORLD)
+        scaling = "strong"
+        parallelism = f"ep{world}"
+    T = B * S
+    n_rot = 4  # rotate inputs: 4 x 64 MiB activations + 304 MB weights per step >> 126 MB L2
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.randn(B, S, 2048, generator=gen, device=dev, dtype=torch.float32).to(dt) for _ in range(n_rot)]
+
+    # ---- stage events (recorded between kernel launches on the launching stream) ----
+    stage_events = []
+
+    def hook(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        stage_events[-1].append((name, ev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        layer(xs[i % n_rot], None, None)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m.stage_hook = hook
+    step_ev = []
+    for i in range(args.steps):
+        stage_events.append([])
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = layer(xs[(args.warmup + i) % n_rot], None, None)
+        e.record()
+        step_ev.append((s, e))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    m.stage_hook = None
+    total_ms = step_ev[0][0].elapsed_time(step_ev[-1][1])     # K steps back to back, first start -> last end
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = T * world / (ms_per_step * 1e-3)
+
+    # per-stage durations (mean over the timed steps)
+    stages = {}
+    for evs in stage_events:
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            stages.setdefault(n1, []).append(e0.elapsed_time(e1))
+    stage_ms = {k: sum(v) / len(v) for k, v in stages.items()}
+
+    # routed rows of the last step (A = sum_t r_t) -> algorithmic FLOPs of the grouped GEMMs
+    ws = m.last_workspace
+    n_rows_local = int(ws.mtiles[: int(ws.n_mtiles.item()), 3].sum().item())  # valid rows in this rank's row space
+    roofline = None
+    if "ffn_gemm1" in stage_ms:
+        flops = n_rows_local * FLOP_PER_ROW_GEMM1
+        ach = flops / (stage_ms["ffn_gemm1"] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("ffn_gemm1_dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        # the step is ~2 ms and the timed region tens of ms: the kernel runs in the burst regime, so the
+        # denominator is the BURST cuBLAS figure (the larger, i.e. stricter, of the two measured peaks)
+        roofline = {"kernel": "ffn_gemm_kernel<SwiGLU> (grouped GEMM-1, tcgen05)", "bound": "tensor", "achieved": ach,
+                    "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_burst"],
+                    "peak_source": f"bf16_tflops (burst) of {peaks['source']}; frac_of_sustained uses bf16_tflops_sustained",
+                    "frac_of_sustained": ach / peaks["tflops_sustained"],
+                    "traffic": traffic, "rows_per_launch": n_rows_local, "flop_per_row": FLOP_PER_ROW_GEMM1,
+                    "avg_launch_ms": stage_ms["ffn_gemm1"]}
+        # the HBM-bound kernels, same events (algorithmic bytes per SURVEY.md 8d / BASELINE.md section 4)
+        A = n_rows_local - T
+        hbm = {"router": T * 4192, "permute": (T + A) * 4096, "combine": (A + T) * 4096 + T * 4096}
+        roofline["hbm_kernels"] = {
+            k: {"achieved_gbs": b / (stage_ms[k2] * 1e-3) / 1e9, "frac": b / (stage_ms[k2] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "bytes": b, "ms": stage_ms[k2]}
+            for k, k2, b in (("router", "router", hbm["router"]),
+                             ("permute", "permute" if "permute" in stage_ms else "ep_dispatch", hbm["permute"]),
+                             ("combine", "combine" if "combine" in stage_ms else "ep_combine", hbm["combine"]))
+            if k2 in stage_ms}
+        roofline["gemm2"] = {"achieved": n_rows_local * FLOP_PER_ROW_GEMM2 / (stage_ms["ffn_gemm2"] * 1e-3) / 1e12,
+                             "unit": "TFLOP/s", "ms": stage_ms["ffn_gemm2"]}
+
+    # ---- e2e: public module call with pinned host buffers, copies inside the timed region ----
+    x_host = [x.cpu().pin_memory() for x in xs[:2]]
+    x_dev = torch.empty_like(xs[0])
+    out_host = None
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(i):
+        nonlocal out_host
+        x_dev.copy_(x_host[i % 2], non_blocking=True)
+        o = layer(x_dev, None, None)
+        if out_host is None:
+            out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
+        for h, t in zip(out_host, o):
+            h.copy_(t, non_blocking=True)
+        return o
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s.record()
+    for i in range(e2e_steps):
+        o = e2e_step(i)
+    e.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(s.elapsed_time(e), 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+    e2e_value = T * world * e2e_steps / (e2e_ms * 1e-3)
+    h2d = x_dev.numel() * x_dev.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in o)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        best, mean, cores, times = cpu_oracle_tokens_per_sec(1024, reps=2, warmup=1)
+        cpu_baseline = {"value": mean, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "oracle port on 1 x 1024 tokens of the same workload, bf16, all host threads, mean of 2"}
+
+    if rank == 0:
+        A = n_rows_local
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "tokens_per_step_global": T * world, "parallelism": parallelism,
+                       "l2": f"no explicit flush: inputs rotate over {n_rot} buffers ({n_rot * T * 4096 >> 20} MiB) and each step "
+                             "streams 304 MB of expert weights + >1 GB of intermediates through the 126 MB L2",
+                       "ffn_rows_rank0": A, "weights": "random N(0, 0.02^2)", "top_p": 0.7},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps},
+            "gpu_launches": KERNELS_PER_STEP * args.steps if world == 1 else None,
+            "roofline": roofline,
+            "stage_ms": stage_ms,
+            "cpu_baseline": cpu_baseline,
+            "peaks": peaks,
+        }
+        if world > 1:
+            line["gpu_launches"] = layer.kernels_per_step * args.steps
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,45 @@ int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_
 int dcmoe_pack_expert(const void* gate_proj, const void* up_proj, const void* down_proj, int group, int part,
                       const dcmoe_config* cfg, void* w13, void* w2, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Expert parallelism (reference: AudioMOELayer.forward with ep_group, core.py:455-457, :467, :480;
+ * group wiring core.py:505-520).  Rank r owns routed experts [r*n_loc, (r+1)*n_loc), n_loc = n_real/world;
+ * gate and shared experts are replicated; every rank routes its own T tokens.  The two all_to_all_single
+ * calls of the reference become peer-memory stores (dispatch) and peer-memory loads (combine) inside the
+ * permute / combine kernels; buffers that peers touch are allocated with dcmoe_ipc_alloc and mapped with
+ * dcmoe_ipc_export / dcmoe_ipc_import (cudaIpc*).  Up to 8 ranks on one NVSwitch node.
+ * Call order per forward on each rank (all launch-only, same stream):
+ *   dcmoe_router -> dcmoe_plan (local counts + block prefix sums)
+ *   -> [all-gather of (counts[0..n_real), T) over ranks: NCCL, done by the caller]
+ *   -> dcmoe_ep_plan -> dcmoe_ep_dispatch -> [barrier] -> dcmoe_grouped_ffn with a config whose
+ *   n_real = n_loc (w13 / w2 hold the local experts + the shared pack) -> [barrier] -> dcmoe_ep_combine.
+ */
+#define DCMOE_MAX_RANKS 8
+#define DCMOE_EP_META_INTS 32
+
+int dcmoe_ipc_alloc(int64_t bytes, void** ptr);
+int dcmoe_ipc_free(void* ptr);
+int dcmoe_ipc_export(const void* ptr, uint8_t* handle64);          /* 64-byte cudaIpcMemHandle_t */
+int dcmoe_ipc_import(const uint8_t* handle64, void** ptr);
+int dcmoe_ipc_close(void* ptr);
+
+/* all_counts: device int32 [world][n_real + 1] (per-rank routed rows per global expert, then the rank's T).
+ * Writes this rank's row-space layout (seg_base, counts of the LOCAL experts, tile table) into `plan` and the
+ * destinations of this rank's rows into ep_meta (device int32 [DCMOE_EP_META_INTS]). */
+int dcmoe_ep_plan(const int32_t* all_counts, int rank, int world, int64_t T, int64_t row_capacity,
+                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, void* stream);
+
+/* peer_x_packed / peer_row_scale: HOST arrays of `world` device pointers (entry `rank` = this rank's own
+ * buffers).  slot_of [T, n_real] receives the row-space row ON THE OWNER of (token, expert), or -1. */
+int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T,
+                      int64_t row_capacity, const dcmoe_config* cfg, const void* plan, const int32_t* ep_meta,
+                      int rank, int world, void* const* peer_x_packed, float* const* peer_row_scale, int32_t* slot_of,
+                      void* stream);
+
+/* peer_y: HOST array of `world` device pointers to the ranks' y buffers.  out [T, H] D. */
+int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32_t* slot_of, int64_t T,
+                     const dcmoe_config* cfg, int world, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,66 @@
+"""Host-side logic of the expert-parallel path on CPU: the layout arithmetic (mirror of ep_plan_kernel) and a
+world_size-2 gloo run of the count exchange that drives it."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from unimoe_audio_b200.ep import ep_layout
+
+
+def _random_counts(world, seed):
+    g = torch.Generator().manual_seed(seed)
+    T = torch.randint(1, 3000, (world,), generator=g).tolist()
+    return [[int(torch.randint(0, T[r] + 1, (1,), generator=g)) for _ in range(8)] + [T[r]] for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_ep_layout_segments_partition_the_owner_row_space(world):
+    n_real, n_loc = 8, 8 // world
+    ac = _random_counts(world, 100 + world)
+    layouts = [ep_layout(ac, r, n_real) for r in range(world)]
+    for e in range(n_real):
+        owner = e // n_loc
+        _, _, seg, tot = layouts[owner]
+        l = e - owner * n_loc
+        # the ranks' destination ranges tile [seg[l], seg[l] + total_e) in rank order, without gaps or overlap
+        cur = seg[l]
+        for r in range(world):
+            base = layouts[r][0][e]
+            assert base == cur
+            assert layouts[r][1][e] == (ac[owner][n_real] + 127) // 128 * 128
+            cur += ac[r][e]
+        assert cur == seg[l] + tot[l] and cur <= seg[l + 1] and seg[l] % 128 == 0
+    for r in range(world):
+        assert layouts[r][2][0] == (ac[r][n_real] + 127) // 128 * 128     # routed rows start after the shared rows
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ac = _random_counts(world, 7)
+    mine = torch.tensor(ac[rank], dtype=torch.int32)
+    gathered = [torch.empty(9, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gathered, mine)                         # the one data-path collective besides the barriers
+    table = torch.stack(gathered).tolist()
+    flag = torch.zeros(1, dtype=torch.int32)
+    dist.all_reduce(flag)                                   # barrier stand-in
+    ret[rank] = (table, ep_layout(table, rank, 8))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_count_exchange_gives_consistent_layouts():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29517, ret), nprocs=world, join=True)
+    t0, l0 = ret[0]
+    t1, l1 = ret[1]
+    assert t0 == t1 == _random_counts(world, 7)
+    # rank 1's rows of every expert start right after rank 0's
+    for e in range(8):
+        assert l1[0][e] == l0[0][e] + t0[0][e]
+        assert l0[1][e] == l1[1][e]

@@ -55,6 +55,16 @@ SIGNATURES = {
     "dcmoe_combine": (c_int, [c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p]),
     "dcmoe_pack_expert": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(DcmoeConfig), c_void_p, c_void_p,
                                   c_void_p]),
+    "dcmoe_ipc_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "dcmoe_ipc_free": (c_int, [c_void_p]),
+    "dcmoe_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "dcmoe_ipc_import": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "dcmoe_ipc_close": (c_int, [c_void_p]),
+    "dcmoe_ep_plan": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p]),
+    "dcmoe_ep_dispatch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
+                                  c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]),
+    "dcmoe_ep_combine": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_int64, POINTER(DcmoeConfig), c_int, c_void_p,
+                                 c_void_p]),
 }
 
 

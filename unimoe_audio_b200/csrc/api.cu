@@ -62,7 +62,6 @@ static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_hint, dcmoe_sizes* sz,
                       dcmoe_plan_layout* l) {
-    const int n_dyn = cfg->n_real + cfg->n_null;
     sz->n_blocks = ceil_div(T, kRouterBlock);
     sz->t_pad = round_up(T, kTileM);
     const int64_t worst = sz->t_pad + (int64_t)cfg->n_real * T + (int64_t)kTileM * cfg->n_real;
@@ -74,9 +73,11 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     }
     sz->max_mtiles = sz->row_capacity / kTileM;
     int64_t off = 0;
-    l->block_counts = off; off = align_up(off + sz->n_blocks * n_dyn * 4, 16);
-    l->block_probs = off;  off = align_up(off + sz->n_blocks * n_dyn * 4, 16);
-    l->block_offsets = off; off = align_up(off + sz->n_blocks * cfg->n_real * 4, 16);
+    // sections are sized for kMaxDyn columns so that the layout does not depend on the expert counts
+    // (expert parallelism runs the FFN with a per-rank config on the same plan buffer)
+    l->block_counts = off; off = align_up(off + sz->n_blocks * kMaxDyn * 4, 16);
+    l->block_probs = off;  off = align_up(off + sz->n_blocks * kMaxDyn * 4, 16);
+    l->block_offsets = off; off = align_up(off + sz->n_blocks * kMaxDyn * 4, 16);
     l->counts = off;       off = align_up(off + kMaxDyn * 4, 16);
     l->seg_base = off;     off = align_up(off + (kMaxDyn + 1) * 4, 16);
     l->n_mtiles = off;     off = align_up(off + 4, 16);
@@ -95,6 +96,7 @@ int launch_permute(const void*, const int32_t*, const void*, int64_t, const dcmo
                    void*, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, void*, cudaStream_t);
 int launch_pack(const void*, const void*, const void*, int, int, const dcmoe_config*, void*, void*, cudaStream_t);
+int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv);
 int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
                     const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
@@ -109,6 +111,14 @@ static int require_device() {
         cudaGetLastError();
         return DCMOE_ERR_CUDA;
     }
+    return DCMOE_OK;
+}
+
+int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv) {
+    dcmoe_plan_layout l;
+    int rc = fill_sizes(cfg, T, row_capacity, sz, &l);
+    if (rc) return rc;
+    *pv = plan_view(plan, l);
     return DCMOE_OK;
 }
 

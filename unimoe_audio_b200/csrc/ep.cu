@@ -1,0 +1,357 @@
+// ep.cu -- expert-parallel dispatch / combine over NVLink peer memory (sm_100a).
+//
+// Reference semantics: AudioMOELayer.forward with an expert-parallel group (core.py:446-493): every rank
+// routes its own tokens, rank r owns routed experts [r*n_loc, (r+1)*n_loc), two all_to_all_single calls on
+// buffers padded to the GLOBAL-MAX capacity (core.py:455-457, :467, :480) carry tokens to the owners and
+// results back.  Here the exchange is fused into the permute and combine kernels:
+//   * dispatch: the permute kernel stores each selected row DIRECTLY into the owner's packed buffer
+//     (st.global on a cudaIpc-mapped peer pointer, 128-bit, one NVLink write per row per expert) at the
+//     row-space slot computed from the all-gathered per-rank counts -- only real rows travel, nothing is
+//     padded to a capacity, and the owner's buffer ends up in the canonical order (rank-major, then
+//     ascending token id) with no receive-side regrouping;
+//   * combine: the combine kernel gathers a token's <= n_real routed rows from the owners' y buffers with
+//     128-bit peer loads (ld.global.nc over NVLink), adds the local shared-expert row in fp32, one store.
+// The only host-visible collectives are an all-gather of (n_real + 1) int32 per rank and two 4-byte
+// all-reduces used as stream-ordered barriers (NCCL, issued from Python).
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dcmoe {
+
+constexpr int kMaxRanks = 8;
+
+struct EpPeers {
+    char* x_packed[kMaxRanks];
+    float* row_scale[kMaxRanks];
+    const char* y[kMaxRanks];
+};
+
+// ep_meta (device int32): [0,16) dest_base[e]  row-space row ON THE OWNER where this rank's rows of expert e start
+//                         [16,32) dest_tpad[e]  t_pad of the owner of expert e
+constexpr int kEpMetaInts = 32;
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// all_counts: [world][n_real + 1] int32 = per-rank routed counts per (global) expert, then that rank's token count
+__global__ void __launch_bounds__(256) ep_plan_kernel(const int32_t* __restrict__ all_counts, int rank, int world,
+                                                      int n_real, int n_loc, int64_t T, int max_mtiles, PlanView pv,
+                                                      int32_t* __restrict__ ep_meta) {
+    __shared__ int s_total[kMaxDyn];     // global rows per expert
+    __shared__ int s_before[kMaxDyn];    // rows of expert e coming from ranks < rank
+    __shared__ int s_seg[kMaxDyn + 1];   // local row-space segment bases (local experts)
+    __shared__ int s_tile0[kMaxDyn + 1];
+    const int stride = n_real + 1;
+    const int t_pad = (int)((T + kTileM - 1) / kTileM) * kTileM;
+    if (threadIdx.x < n_real) {
+        const int e = threadIdx.x;
+        int tot = 0, before = 0;
+        for (int r = 0; r < world; ++r) {
+            const int c = all_counts[r * stride + e];
+            if (r < rank) before += c;
+            tot += c;
+        }
+        s_total[e] = tot;
+        s_before[e] = before;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_real) {
+        // destination of MY rows of expert e on its owner
+        const int e = threadIdx.x;
+        const int owner = e / n_loc;
+        const int owner_T = all_counts[owner * stride + n_real];
+        const int owner_tpad = (owner_T + kTileM - 1) / kTileM * kTileM;
+        int base = owner_tpad;
+        for (int q = owner * n_loc; q < e; ++q) base += (s_total[q] + kTileM - 1) / kTileM * kTileM;
+        ep_meta[e] = base + s_before[e];
+        ep_meta[16 + e] = owner_tpad;
+    }
+    if (threadIdx.x == 0) {
+        int row = t_pad, tile = t_pad / kTileM;
+        for (int l = 0; l < n_loc; ++l) {
+            const int e = rank * n_loc + l;
+            s_seg[l] = row;
+            s_tile0[l] = tile;
+            pv.seg_base[l] = row;
+            pv.counts[l] = s_total[e];
+            const int nt = (s_total[e] + kTileM - 1) / kTileM;
+            row += nt * kTileM;
+            tile += nt;
+        }
+        s_seg[n_loc] = row;
+        s_tile0[n_loc] = tile;
+        pv.seg_base[n_loc] = row;
+        *pv.n_mtiles = tile < max_mtiles ? tile : max_mtiles;
+    }
+    __syncthreads();
+    const int n_shared_tiles = t_pad / kTileM;
+    const int total = s_tile0[n_loc];
+    for (int i = threadIdx.x; i < total && i < max_mtiles; i += blockDim.x) {
+        dcmoe_mtile mt;
+        if (i < n_shared_tiles) {
+            mt.a_row = i * kTileM;
+            mt.out_row = i * kTileM;
+            mt.group = n_loc;
+            const int64_t left = T - (int64_t)i * kTileM;
+            mt.rows = (int)(left < kTileM ? left : kTileM);
+        } else {
+            int l = 0;
+            while (l + 1 < n_loc && i >= s_tile0[l + 1]) ++l;
+            const int local = i - s_tile0[l];
+            mt.out_row = s_seg[l] + local * kTileM;
+            mt.a_row = mt.out_row - t_pad;
+            mt.group = l;
+            const int left = s_total[rank * n_loc + l] - local * kTileM;
+            mt.rows = left < kTileM ? left : kTileM;
+        }
+        pv.mtiles[i] = mt;
+    }
+}
+
+template <int ESIZE>
+__global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict__ x, const int32_t* __restrict__ mask,
+                                                          const char* __restrict__ gw, int64_t T, int H, int n_real,
+                                                          int n_dyn, int n_fix, int n_loc, int rank,
+                                                          const int32_t* __restrict__ block_offsets,
+                                                          const int32_t* __restrict__ ep_meta, EpPeers peers,
+                                                          int32_t* __restrict__ slot_of) {
+    __shared__ int s_m[kRouterBlock][kMaxDyn];
+    __shared__ int s_slot[kRouterBlock][kMaxDyn];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = n_dyn + n_fix;
+    const int64_t tok0 = (int64_t)blockIdx.x * kRouterBlock;
+    auto load_gw = [&](int64_t t, int j) -> float {
+        if (ESIZE == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gw)[t * E + j]);
+        return reinterpret_cast<const float*>(gw)[t * E + j];
+    };
+    for (int i = tid; i < kRouterBlock * n_real; i += 128) {
+        const int tl = i / n_real, e = i % n_real;
+        const int64_t t = tok0 + tl;
+        s_m[tl][e] = (t < T) ? mask[t * E + e] : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < kRouterBlock * n_real; i += 128) {
+        const int tl = i / n_real, e = i % n_real;
+        const int64_t t = tok0 + tl;
+        int rk = 0;
+        for (int q = 0; q < tl; ++q) rk += s_m[q][e];
+        int slot = -1;
+        if (s_m[tl][e]) {
+            slot = ep_meta[e] + block_offsets[(int64_t)blockIdx.x * n_real + e] + rk;   // row on the owner
+            const float w = load_gw(t, e);
+            float* sc = peers.row_scale[e / n_loc];
+            sc[2 * (int64_t)slot] = w;
+            sc[2 * (int64_t)slot + 1] = w;
+        }
+        s_slot[tl][e] = slot;
+        if (t < T) slot_of[t * n_real + e] = slot;
+    }
+    if (tid < kRouterBlock) {
+        const int64_t t = tok0 + tid;
+        if (t < T) {
+            float* sc = peers.row_scale[rank];
+            sc[2 * t] = load_gw(t, n_dyn);
+            sc[2 * t + 1] = n_fix > 1 ? load_gw(t, n_dyn + 1) : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int n_vec = H * ESIZE / 16;
+    for (int q = 0; q < kRouterBlock / 4; ++q) {
+        const int tl = warp * (kRouterBlock / 4) + q;
+        const int64_t t = tok0 + tl;
+        if (t >= T) continue;
+        int n_dst = 0;
+        for (int e = 0; e < n_real; ++e) n_dst += s_slot[tl][e] >= 0;
+        if (n_dst == 0) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(x + t * (int64_t)H * ESIZE);
+        for (int c0 = 0; c0 < n_vec; c0 += 256) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                if (c < n_vec) v[u] = ld_nc_v4(src + c);
+            }
+            for (int e = 0; e < n_real; ++e) {
+                const int slot = s_slot[tl][e];
+                if (slot < 0) continue;
+                uint4* dst = reinterpret_cast<uint4*>(peers.x_packed[e / n_loc] +
+                                                      (int64_t)(slot - ep_meta[16 + e]) * H * ESIZE);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    if (c < n_vec) st_na_v4(dst + c, v[u]);   // local HBM or NVLink peer write
+                }
+            }
+        }
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) ep_combine_kernel(const char* __restrict__ y_local, EpPeers peers,
+                                                         const int32_t* __restrict__ slot_of, int64_t T, int H,
+                                                         int n_real, int n_loc, char* __restrict__ out) {
+    constexpr int ESIZE = BF16 ? 2 : 4;
+    constexpr int PER = 16 / ESIZE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
+    if (t >= T) return;
+    const int my_slot = lane < n_real ? slot_of[t * n_real + lane] : -1;
+    const int n_vec = H * ESIZE / 16;
+    const int64_t row_bytes = (int64_t)H * ESIZE;
+    auto accumulate = [&](float (&acc)[8][PER], const uint4 (&v)[8], bool init) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float f[8];
+            if (BF16) {
+                f[0] = bf16lo(v[u].x); f[1] = bf16hi(v[u].x); f[2] = bf16lo(v[u].y); f[3] = bf16hi(v[u].y);
+                f[4] = bf16lo(v[u].z); f[5] = bf16hi(v[u].z); f[6] = bf16lo(v[u].w); f[7] = bf16hi(v[u].w);
+            } else {
+                f[0] = __uint_as_float(v[u].x); f[1] = __uint_as_float(v[u].y);
+                f[2] = __uint_as_float(v[u].z); f[3] = __uint_as_float(v[u].w);
+            }
+#pragma unroll
+            for (int i = 0; i < PER; ++i) acc[u][i] = init ? f[i] : acc[u][i] + f[i];
+        }
+    };
+    for (int c0 = 0; c0 < n_vec; c0 += 256) {
+        float acc[8][PER];
+        uint4 v[8];
+        const uint4* src = reinterpret_cast<const uint4*>(y_local + t * row_bytes);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            v[u] = c < n_vec ? ld_nc_v4(src + c) : make_uint4(0, 0, 0, 0);
+        }
+        accumulate(acc, v, true);
+        for (int e = 0; e < n_real; ++e) {
+            const int slot = __shfl_sync(kFull, my_slot, e);
+            if (slot < 0) continue;
+            const uint4* s2 = reinterpret_cast<const uint4*>(peers.y[e / n_loc] + (int64_t)slot * row_bytes);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                v[u] = c < n_vec ? ld_nc_v4(s2 + c) : make_uint4(0, 0, 0, 0);   // local HBM or NVLink peer read
+            }
+            accumulate(acc, v, false);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + t * row_bytes);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c >= n_vec) continue;
+            uint4 o;
+            if (BF16) {
+                o.x = pack_bf16(acc[u][0], acc[u][1]);
+                o.y = pack_bf16(acc[u][2 % PER], acc[u][3 % PER]);
+                o.z = pack_bf16(acc[u][4 % PER], acc[u][5 % PER]);
+                o.w = pack_bf16(acc[u][6 % PER], acc[u][7 % PER]);
+            } else {
+                o.x = __float_as_uint(acc[u][0]); o.y = __float_as_uint(acc[u][1]);
+                o.z = __float_as_uint(acc[u][2]); o.w = __float_as_uint(acc[u][3]);
+            }
+            st_na_v4(dst + c, o);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace dcmoe
+
+using namespace dcmoe;
+
+// defined in api.cu
+namespace dcmoe {
+int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv);
+}
+
+extern "C" {
+
+int dcmoe_ipc_alloc(int64_t bytes, void** ptr) {
+    if (!ptr || bytes <= 0) { set_error("dcmoe_ipc_alloc: bad arguments"); return DCMOE_ERR_INVALID; }
+    return check_cuda(cudaMalloc(ptr, (size_t)bytes), "cudaMalloc (ipc buffer)");
+}
+int dcmoe_ipc_free(void* ptr) { return check_cuda(cudaFree(ptr), "cudaFree (ipc buffer)"); }
+int dcmoe_ipc_export(const void* ptr, uint8_t* handle64) {
+    if (!ptr || !handle64) { set_error("dcmoe_ipc_export: NULL argument"); return DCMOE_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    int rc = check_cuda(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)), "cudaIpcGetMemHandle");
+    if (rc) return rc;
+    memcpy(handle64, &h, 64);
+    return DCMOE_OK;
+}
+int dcmoe_ipc_import(const uint8_t* handle64, void** ptr) {
+    if (!ptr || !handle64) { set_error("dcmoe_ipc_import: NULL argument"); return DCMOE_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return check_cuda(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+int dcmoe_ipc_close(void* ptr) { return check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle"); }
+
+int dcmoe_ep_plan(const int32_t* all_counts, int rank, int world, int64_t T, int64_t row_capacity,
+                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, void* stream) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (!all_counts || !plan || !ep_meta || world < 1 || world > kMaxRanks || rank < 0 || rank >= world ||
+        cfg->n_real % world != 0) {
+        set_error("dcmoe_ep_plan: bad arguments (world=%d rank=%d n_real=%d)", world, rank, cfg->n_real);
+        return DCMOE_ERR_INVALID;
+    }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = ep_plan_view(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
+    ep_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(all_counts, rank, world, cfg->n_real, cfg->n_real / world, T,
+                                                        (int)sz.max_mtiles, pv, ep_meta);
+    return check_cuda(cudaGetLastError(), "ep_plan_kernel launch");
+}
+
+int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T,
+                      int64_t row_capacity, const dcmoe_config* cfg, const void* plan, const int32_t* ep_meta,
+                      int rank, int world, void* const* peer_x_packed, float* const* peer_row_scale, int32_t* slot_of,
+                      void* stream) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (T == 0) return DCMOE_OK;
+    if (!x || !expert_mask || !global_weight || !plan || !ep_meta || !peer_x_packed || !peer_row_scale || !slot_of ||
+        world < 1 || world > kMaxRanks || cfg->n_real % world != 0) {
+        set_error("dcmoe_ep_dispatch: bad arguments");
+        return DCMOE_ERR_INVALID;
+    }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = ep_plan_view(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
+    EpPeers peers{};
+    for (int r = 0; r < world; ++r) { peers.x_packed[r] = (char*)peer_x_packed[r]; peers.row_scale[r] = peer_row_scale[r]; }
+    const int n_dyn = cfg->n_real + cfg->n_null;
+    dim3 grid((unsigned)sz.n_blocks), block(128);
+    if (cfg->dtype == DCMOE_BF16)
+        ep_dispatch_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of);
+    else
+        ep_dispatch_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of);
+    return check_cuda(cudaGetLastError(), "ep_dispatch_kernel launch");
+}
+
+int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32_t* slot_of, int64_t T,
+                     const dcmoe_config* cfg, int world, void* out, void* stream) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (T == 0) return DCMOE_OK;
+    if (!y_local || !peer_y || !slot_of || !out || world < 1 || world > kMaxRanks || cfg->n_real % world != 0) {
+        set_error("dcmoe_ep_combine: bad arguments");
+        return DCMOE_ERR_INVALID;
+    }
+    EpPeers peers{};
+    for (int r = 0; r < world; ++r) peers.y[r] = (const char*)peer_y[r];
+    dim3 grid((unsigned)ceil_div(T, 8)), block(256);
+    if (cfg->dtype == DCMOE_BF16)
+        ep_combine_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,
+            cfg->hidden_size, cfg->n_real, cfg->n_real / world, (char*)out);
+    else
+        ep_combine_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,
+            cfg->hidden_size, cfg->n_real, cfg->n_real / world, (char*)out);
+    return check_cuda(cudaGetLastError(), "ep_combine_kernel launch");
+}
+
+}  // extern "C"

@@ -1,6 +1,6 @@
 // plan_permute_combine.cu -- the integer / byte-moving side of the DCMoE layer (sm_100a).
 //
-//   plan_kernel     exact per-expert histogram (from the router's per-block counts) -> exclusive
+//   plan_kernel     (one launch, also finishes the aux loss) exact per-expert histogram (from the router's per-block counts) -> exclusive
 //                   prefix sums over token blocks -> 128-row aligned expert segments -> m-tile table
 //                   for the grouped GEMMs -> aux loss.  Replaces reference core.py:455 (capacity =
 //                   mask.sum(0).max(); here exact counts, no padding to the max) and finishes
@@ -23,31 +23,66 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
+template <bool BF16>
 __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int n_real, int64_t T, int t_pad,
                                                     int max_mtiles, PlanView pv) {
     __shared__ int s_counts[kMaxDyn];
     __shared__ int s_seg[kMaxDyn + 1];
     __shared__ int s_tile0[kMaxDyn + 1];
+    __shared__ double s_term[kMaxDyn];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp < n_real) {  // exclusive scan of expert `warp` over token blocks
+    if (warp < n_real) {
+        // exclusive scan of expert `warp` over token blocks: 8 consecutive blocks per lane, 256 per step
         const int e = warp;
         int carry = 0;
-        for (int base = 0; base < n_blocks; base += 32) {
-            const int b = base + lane;
-            const int v = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
-            int incl = v;
+        for (int base = 0; base < n_blocks; base += 256) {
+            int v[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = base + lane * 8 + i;
+                v[i] = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
+                sum += v[i];
+            }
+            int incl = sum;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 int o = __shfl_up_sync(kFull, incl, off);
                 if (lane >= off) incl += o;
             }
-            if (b < n_blocks) pv.block_offsets[(int64_t)b * n_real + e] = carry + incl - v;
+            int run = carry + incl - sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = base + lane * 8 + i;
+                if (b < n_blocks) pv.block_offsets[(int64_t)b * n_real + e] = run;
+                run += v[i];
+            }
             carry += __shfl_sync(kFull, incl, 31);
         }
         if (lane == 0) {
             s_counts[e] = carry;
             pv.counts[e] = carry;
+        }
+    } else if (warp >= 16 && warp < 16 + n_dyn) {
+        // aux loss (core.py:376-389, aux_balance_weight = None): column means over tokens.  Fixed reduction
+        // shape (lane-strided partial sums, xor tree) -> bit-stable run to run.
+        const int j = warp - 16;
+        double ps = 0.0;
+        long long ts = 0;
+        for (int b = lane; b < n_blocks; b += 32) {
+            ps += (double)pv.block_probs[(int64_t)b * n_dyn + j];
+            ts += pv.block_counts[(int64_t)b * n_dyn + j];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            ps += __shfl_xor_sync(kFull, ps, off);
+            ts += __shfl_xor_sync(kFull, ts, off);
+        }
+        if (lane == 0) {
+            float tpe = (float)((double)ts / (double)T);          // torch.mean(expert_mask.float(), 0)
+            float rp = (float)(ps / (double)T);                   // torch.mean(global_weight, 0) ...
+            if (BF16) rp = bf16_round(rp);                        // ... is a D tensor (bf16 rounds here)
+            s_term[j] = (double)(tpe * rp);
         }
     }
     __syncthreads();
@@ -66,6 +101,9 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         s_tile0[n_real] = tile;
         pv.seg_base[n_real] = row;
         *pv.n_mtiles = tile < max_mtiles ? tile : max_mtiles;
+        double acc = 0.0;
+        for (int j = 0; j < n_dyn; ++j) acc += s_term[j];         // fixed left-to-right order over experts
+        *pv.aux_loss = (float)acc * (float)n_dyn;
     }
     __syncthreads();
     // m-tile table: shared-expert tiles first (largest group first), then routed experts
@@ -91,31 +129,6 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         }
         pv.mtiles[i] = mt;
     }
-}
-
-// aux loss (core.py:376-389, aux_balance_weight = None): column means over tokens and their dot product
-template <bool BF16>
-__global__ void aux_kernel(int n_blocks, int n_dyn, int64_t T, PlanView pv) {
-    // one warp; lane j < n_dyn owns column j.  Column sums are re-done here in a fixed order
-    // (sequential over blocks per lane) so that the result is independent of the launch shape.
-    const int j = threadIdx.x;
-    double term = 0.0;
-    if (j < n_dyn) {
-        double ps = 0.0;
-        long long ts = 0;
-        for (int b = 0; b < n_blocks; ++b) {
-            ps += (double)pv.block_probs[(int64_t)b * n_dyn + j];
-            ts += pv.block_counts[(int64_t)b * n_dyn + j];
-        }
-        float tpe = (float)((double)ts / (double)T);          // torch.mean(expert_mask.float(), 0)
-        float rp = (float)(ps / (double)T);                   // torch.mean(global_weight, 0) ...
-        if (BF16) rp = bf16_round(rp);                        // ... is a D tensor (bf16 rounds here)
-        term = (double)(tpe * rp);
-    }
-    // fixed left-to-right order over experts
-    double acc = 0.0;
-    for (int i = 0; i < n_dyn; ++i) acc += __shfl_sync(kFull, term, i);
-    if (j == 0) *pv.aux_loss = (float)acc * (float)n_dyn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -306,14 +319,11 @@ __global__ void pack_kernel(const char* __restrict__ gate_proj, const char* __re
 
 int launch_plan(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv, cudaStream_t stream) {
     const int n_dyn = cfg->n_real + cfg->n_null;
-    plan_kernel<<<1, 1024, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv);
-    int rc = check_cuda(cudaGetLastError(), "plan_kernel launch");
-    if (rc) return rc;
     if (cfg->dtype == DCMOE_BF16)
-        aux_kernel<true><<<1, 32, 0, stream>>>((int)sz.n_blocks, n_dyn, T, pv);
+        plan_kernel<true><<<1, 1024, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv);
     else
-        aux_kernel<false><<<1, 32, 0, stream>>>((int)sz.n_blocks, n_dyn, T, pv);
-    return check_cuda(cudaGetLastError(), "aux_kernel launch");
+        plan_kernel<false><<<1, 1024, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv);
+    return check_cuda(cudaGetLastError(), "plan_kernel launch");
 }
 
 int launch_permute(const void* x, const int32_t* expert_mask, const void* gw, int64_t T, const dcmoe_config* cfg,

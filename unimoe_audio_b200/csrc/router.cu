@@ -62,7 +62,7 @@ __device__ __forceinline__ float rnd(float v) {
 // softmax over lanes [0, n) of a 16-lane group; lanes >= n must hold -inf.  Sequential sum in
 // lane order, multiply by the reciprocal, round to D -- the ATen CPU order.
 template <bool BF16>
-__device__ __forceinline__ float softmax_lanes(float v, int j, int n) {
+__device__ __forceinline__ float softmax_lanes(float v, int j, const int n) {
     float m = v;
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, off, 16));
@@ -71,8 +71,7 @@ __device__ __forceinline__ float softmax_lanes(float v, int j, int n) {
     float s = __shfl_sync(kFull, e, 0, 16);
 #pragma unroll
     for (int i = 1; i < kMaxDyn; ++i) {
-        float ei = __shfl_sync(kFull, e, i, 16);
-        if (i < n) s = __fadd_rn(s, ei);
+        if (i < n) s = __fadd_rn(s, __shfl_sync(kFull, e, i, 16));   // n is warp-uniform
     }
     float inv = __fdiv_rn(1.0f, s);
     return rnd<BF16>(__fmul_rn(e, inv));
@@ -87,14 +86,12 @@ __device__ __forceinline__ float row_sum8_lanes(float d, int n) {
         acc[k] = 0.0f;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            float v = __shfl_sync(kFull, d, 8 * i + k, 16);
-            if (i < n8) acc[k] = __fadd_rn(acc[k], v);
+            if (i < n8) acc[k] = __fadd_rn(acc[k], __shfl_sync(kFull, d, 8 * i + k, 16));
         }
     }
 #pragma unroll
     for (int i = 0; i < kMaxDyn; ++i) {
-        float v = __shfl_sync(kFull, d, i, 16);
-        if (i >= 8 * n8 && i < n) acc[0] = __fadd_rn(acc[0], v);
+        if (i >= 8 * n8 && i < n) acc[0] = __fadd_rn(acc[0], __shfl_sync(kFull, d, i, 16));
     }
 #pragma unroll
     for (int k = 1; k < 8; ++k) acc[0] = __fadd_rn(acc[0], acc[k]);
@@ -107,10 +104,12 @@ struct RouteConsts {
 };
 
 // Route one token per 16-lane group.  l = logit of lane j (D-representable fp32), am = padding mask.
-template <bool BF16>
+// NDYN / NE > 0 fix the expert counts at compile time (the reference config: 9 dynamic + 2 shared), which
+// trims every shuffle loop to its real length; 0 = read them from rc.
+template <bool BF16, int NDYN, int NE>
 __device__ __forceinline__ void route_token(float l, int j, int half, int am, const RouteConsts& rc, int& raw_out,
                                             int& mask_out, float& gw_out, float& ga_out) {
-    const int n_dyn = rc.n_dyn, E = rc.E;
+    const int n_dyn = NDYN ? NDYN : rc.n_dyn, E = NE ? NE : rc.E;
     const float ninf = __int_as_float(0xff800000);
     const bool dyn = j < n_dyn;
     // ---- Top-P count (core.py:162-166) ----
@@ -118,18 +117,20 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
     int rank = 0;
 #pragma unroll
     for (int i = 0; i < kMaxDyn; ++i) {
-        float pi = __shfl_sync(kFull, p, i, 16);
-        if (i < n_dyn) rank += (pi > p) || (pi == p && i < j);
+        if (i < n_dyn) {
+            float pi = __shfl_sync(kFull, p, i, 16);
+            rank += (pi > p) || (pi == p && i < j);
+        }
     }
     int raw = 1;
     float run = 0.0f;
 #pragma unroll
     for (int r = 0; r < kMaxDyn; ++r) {
-        unsigned b = __ballot_sync(kFull, dyn && rank == r);
-        b = (b >> (half * 16)) & 0xffffu;
-        int src = __ffs(b) - 1;
-        float val = __shfl_sync(kFull, p, src & 15, 16);
         if (r < n_dyn) {
+            unsigned b = __ballot_sync(kFull, dyn && rank == r);
+            b = (b >> (half * 16)) & 0xffffu;
+            int src = __ffs(b) - 1;
+            float val = __shfl_sync(kFull, p, src & 15, 16);
             run = __fadd_rn(run, val);
             float c = rnd<BF16>(run);
             raw += !(c >= rc.thr_p);
@@ -160,7 +161,13 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
         const float ratio = rnd<BF16>(__fdiv_rn(diff, fac));
         const bool drop = ratio > rc.thr_eps;
         const float g = (dyn && !drop) ? rem : ninf;
-        const float sm = softmax_lanes<BF16>(g, j, n_dyn);
+        // The softmax of core.py:118 has max == thr, so e[bi] = exp(0) = 1 exactly and every dropped or
+        // already selected entry contributes exp(-inf) = 0 exactly: unless another remaining logit is within
+        // 2 % of thr (a "near tie", ~3 % of iterations) the sum is exactly 1 and the multiplier exactly 1.
+        // Skip the exp/sum/div then (warp-uniform test); the result is bit-identical to the full softmax.
+        const bool near_tie = (g != ninf) && (j != bi) && (it < k);
+        float sm = 1.0f;
+        if (__any_sync(kFull, near_tie)) sm = softmax_lanes<BF16>(g, j, n_dyn);
         if (it < k && j == bi) {
             rw = sm;
             sel = 1;
@@ -190,7 +197,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <bool BF16>
+template <bool BF16, int NDYN, int NE>
 __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_, const void* __restrict__ wg_,
                                                      const void* __restrict__ logits_in_,
                                                      const int32_t* __restrict__ attn_mask, int64_t T, int H,
@@ -205,7 +212,8 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t tok0 = (int64_t)blockIdx.x * kRouterBlock;
-    const int E = rc.E;
+    const int E = NE ? NE : rc.E;
+    const int n_dyn_k = NDYN ? NDYN : rc.n_dyn;
 
     if (logits_in_ == nullptr) {
         const int Kq = H >> 2;  // columns per warp
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
         const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
         int raw, mk;
         float gw, ga;
-        route_token<BF16>(l, j, half, am, rc, raw, mk, gw, ga);
+        route_token<BF16, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
         if (valid && j < E) {
             if constexpr (BF16) {
                 ((__nv_bfloat16*)logits_out)[t * E + j] = __float2bfloat16_rn(l);
@@ -323,11 +331,11 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
             expert_mask[t * E + j] = mk;
             if (j == 0) top_k[t] = raw;
         }
-        s_cnt[tl][j] = (valid && j < rc.n_dyn) ? mk : 0;
-        s_prob[tl][j] = (valid && j < rc.n_dyn) ? ga : 0.0f;
+        s_cnt[tl][j] = (valid && j < n_dyn_k) ? mk : 0;
+        s_prob[tl][j] = (valid && j < n_dyn_k) ? ga : 0.0f;
     }
     __syncthreads();
-    if (tid < rc.n_dyn) {  // fixed-order block partials -> deterministic aux loss and exact counts
+    if (tid < n_dyn_k) {  // fixed-order block partials -> deterministic aux loss and exact counts
         int cnt = 0;
         float pr = 0.0f;
 #pragma unroll
@@ -335,8 +343,8 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
             cnt += s_cnt[r][tid];
             pr = __fadd_rn(pr, s_prob[r][tid]);
         }
-        block_counts[(int64_t)blockIdx.x * rc.n_dyn + tid] = cnt;
-        block_probs[(int64_t)blockIdx.x * rc.n_dyn + tid] = pr;
+        block_counts[(int64_t)blockIdx.x * n_dyn_k + tid] = cnt;
+        block_probs[(int64_t)blockIdx.x * n_dyn_k + tid] = pr;
     }
 }
 
@@ -358,15 +366,17 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     rc.finfo_min = bf16 ? -3.3895313892515355e38f : -3.4028234663852886e38f;
     const int64_t n_blocks = ceil_div(T, kRouterBlock);
     dim3 grid((unsigned)n_blocks), block(128);
+#define DCMOE_LAUNCH_ROUTER(BF, ND, NE_)                                                                              \
+    router_kernel<BF, ND, NE_><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc, \
+                                                           logits_out, top_k, expert_mask, global_weight,            \
+                                                           block_counts, block_probs)
+    const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
     if (bf16) {
-        router_kernel<true><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc,
-                                                        logits_out, top_k, expert_mask, global_weight, block_counts,
-                                                        block_probs);
+        if (ref_shape) DCMOE_LAUNCH_ROUTER(true, 9, 11); else DCMOE_LAUNCH_ROUTER(true, 0, 0);
     } else {
-        router_kernel<false><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc,
-                                                         logits_out, top_k, expert_mask, global_weight, block_counts,
-                                                         block_probs);
+        if (ref_shape) DCMOE_LAUNCH_ROUTER(false, 9, 11); else DCMOE_LAUNCH_ROUTER(false, 0, 0);
     }
+#undef DCMOE_LAUNCH_ROUTER
     return check_cuda(cudaGetLastError(), "router_kernel launch");
 }
 

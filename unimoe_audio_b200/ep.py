@@ -1,0 +1,308 @@
+"""Expert-parallel DCMoE (reference: AudioMOELayer.forward with an ep_group, core.py:446-493; group wiring
+core.py:505-520).
+
+One process per GPU.  Rank r owns routed experts [r*n_loc, (r+1)*n_loc) (core.py:505), the gate and the shared
+experts are replicated, every rank routes its own tokens.  Per forward and per rank:
+
+    router -> local plan -> all-gather of (counts, T)  [NCCL, 36 bytes per rank]
+           -> ep_plan -> ep_dispatch (rows stored straight into the owners' packed buffers over NVLink)
+           -> barrier -> grouped FFN on the rows this rank owns (tcgen05) -> barrier
+           -> ep_combine (routed rows gathered from the owners' y buffers over NVLink + local shared row)
+
+Buffers touched by peers (x_packed, y, row_scale) are allocated with ``dcmoe_ipc_alloc`` and mapped into
+every rank with cudaIpc handles exchanged once per workspace.  ``LocalRanks`` runs the same kernels for R
+virtual ranks inside one process on one GPU (peer pointers are then ordinary local pointers); it is what the
+single-GPU tests use, as separate processes spinning on one GPU is not allowed on the test boxes.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import replace
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from .dcmoe import DCMoE
+from .ops import LayerDims, Workspace
+
+EP_META_INTS = 32
+
+
+def ep_layout(all_counts: Sequence[Sequence[int]], rank: int, n_real: int):
+    """Host mirror of ``ep_plan_kernel`` (csrc/ep.cu): from the all-gathered [world][n_real+1] table
+    (per-rank rows per global expert, then the rank's token count) return
+    (dest_base[e], dest_tpad[e], local_seg_base[l], local_totals[l]) for `rank`."""
+    world = len(all_counts)
+    n_loc = n_real // world
+    pad = lambda v: (v + 127) // 128 * 128  # noqa: E731
+    total = [sum(all_counts[r][e] for r in range(world)) for e in range(n_real)]
+    before = [sum(all_counts[r][e] for r in range(rank)) for e in range(n_real)]
+    dest_base, dest_tpad = [], []
+    for e in range(n_real):
+        owner = e // n_loc
+        tp = pad(all_counts[owner][n_real])
+        base = tp + sum(pad(total[q]) for q in range(owner * n_loc, e))
+        dest_base.append(base + before[e])
+        dest_tpad.append(tp)
+    seg, row = [], pad(all_counts[rank][n_real])
+    for l in range(n_loc):
+        seg.append(row)
+        row += pad(total[rank * n_loc + l])
+    seg.append(row)
+    return dest_base, dest_tpad, seg, [total[rank * n_loc + l] for l in range(n_loc)]
+
+
+class _RawCuda:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _wrap(ptr: int, nbytes: int, dtype, shape, device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device).view(dtype).view(shape)
+
+
+class EpWorkspace(Workspace):
+    """Workspace whose peer-visible buffers come from dcmoe_ipc_alloc (exportable with cudaIpcGetMemHandle)."""
+
+    def __init__(self, dims: LayerDims, dtype, T: int, device, row_capacity: int, ipc: bool):
+        super().__init__(dims, dtype, T, device, row_capacity, alloc_peer_visible=not ipc)
+        self.ep_meta = torch.zeros(EP_META_INTS, dtype=torch.int32, device=self.device)
+        self.ipc = ipc
+        self._raw = {}
+        if ipc:
+            lib = _lib.load()
+            es = torch.empty((), dtype=dtype).element_size()
+            with torch.cuda.device(self.device):
+                for name, dt, esz in (("x_packed", dtype, es), ("y", dtype, es), ("row_scale", torch.float32, 4)):
+                    shape = self.shapes[name]
+                    nbytes = shape[0] * shape[1] * esz
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.dcmoe_ipc_alloc(nbytes, ctypes.byref(p)), "dcmoe_ipc_alloc")
+                    self._raw[name] = (p.value, nbytes)
+                    setattr(self, name, _wrap(p.value, nbytes, dt, shape, self.device))
+            self.row_scale.zero_()
+
+    def export_handles(self) -> dict:
+        lib = _lib.load()
+        out = {}
+        for name, (ptr, _n) in self._raw.items():
+            buf = (ctypes.c_uint8 * 64)()
+            _lib.check(lib.dcmoe_ipc_export(ptr, buf), "dcmoe_ipc_export")
+            out[name] = bytes(buf)
+        return out
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            lib = _lib.load()
+            for ptr, _n in self._raw.values():
+                lib.dcmoe_ipc_free(ptr)
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class ExpertParallelDCMoE:
+    """Expert-parallel wrapper around a :class:`DCMoE` that holds (at least) this rank's weights.
+
+    ``group`` is a torch.distributed process group (NCCL) of up to 8 ranks on one node; ``rank`` / ``world``
+    default to the group's.  The call signature and the returned 6-tuple are those of the reference block."""
+
+    def __init__(self, module: DCMoE, group=None, rank: Optional[int] = None, world: Optional[int] = None):
+        import torch.distributed as dist
+
+        self.m = module
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        d = module.dims
+        if d.n_real % self.world != 0 or self.world > 8:
+            raise ValueError(f"num_experts ({d.n_real}) must be divisible by ep_size ({self.world}) (core.py:505), ep_size <= 8")
+        self.n_loc = d.n_real // self.world
+        self.local_dims = replace(d, n_real=self.n_loc)
+        self._w13 = self._w2 = None
+        self.ws: Optional[EpWorkspace] = None
+        self._peer = None
+        self._imported = []
+        self._flag = None
+        self.kernels_per_step = 7  # router, plan, ep_plan, ep_dispatch, ffn gemm-1, ffn gemm-2, ep_combine
+        self.row_capacity = 0
+
+    # ------------------------------------------------------------------ setup
+    def pack_local_weights(self):
+        if self._w13 is not None:
+            return
+        m, d, ld = self.m, self.m.dims, self.local_dims
+        p = m.gate.weight
+        G = self.n_loc + 1
+        w13 = torch.empty((G, 2 * d.dynamic_intermediate_size, d.hidden_size), dtype=p.dtype, device=p.device)
+        w2 = torch.empty((G, d.hidden_size, d.dynamic_intermediate_size), dtype=p.dtype, device=p.device)
+        routed, shared = m._expert_params()
+        for l in range(self.n_loc):
+            e = self.rank * self.n_loc + l
+            ex = routed[e] if len(routed) == d.n_real else routed[l]   # full module or local-experts-only module
+            ops.pack_expert(ex.gate_proj.weight.detach().contiguous(), ex.up_proj.weight.detach().contiguous(),
+                            ex.down_proj.weight.detach().contiguous(), l, 0, ld, w13, w2)
+        for i, ex in enumerate(shared):
+            ops.pack_expert(ex.gate_proj.weight.detach().contiguous(), ex.up_proj.weight.detach().contiguous(),
+                            ex.down_proj.weight.detach().contiguous(), self.n_loc, i, ld, w13, w2)
+        self._w13, self._w2 = w13, w2
+
+    def default_row_capacity(self, T: int, T_global: int) -> int:
+        t_pad = (T + 127) // 128 * 128
+        return t_pad + self.n_loc * T_global + 128 * self.n_loc
+
+    def ensure_workspace(self, T: int, dtype, device, ipc: bool, T_global: Optional[int] = None) -> EpWorkspace:
+        cap = self.row_capacity or self.default_row_capacity(T, T_global if T_global is not None else T * self.world)
+        if self.ws is None or self.ws.T != T or self.ws.dtype != dtype or self.ws.row_capacity != cap:
+            self.ws = EpWorkspace(self.m.dims, dtype, T, device, cap, ipc)
+            self._peer = None
+        self.m.last_workspace = self.ws
+        return self.ws
+
+    def set_peers(self, x_packed: List[int], row_scale: List[int], y: List[int]):
+        arr = lambda v: (ctypes.c_void_p * len(v))(*v)  # noqa: E731
+        self._peer = (arr(x_packed), arr(row_scale), arr(y))
+
+    def _exchange_handles(self):
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        mine = self.ws.export_handles()
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        ptrs = {"x_packed": [], "row_scale": [], "y": []}
+        for r in range(self.world):
+            for name in ptrs:
+                if r == self.rank:
+                    ptrs[name].append(self.ws._raw[name][0])
+                else:
+                    p = ctypes.c_void_p()
+                    buf = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r][name])
+                    _lib.check(lib.dcmoe_ipc_import(buf, ctypes.byref(p)), "dcmoe_ipc_import")
+                    self._imported.append(p.value)
+                    ptrs[name].append(p.value)
+        self.set_peers(ptrs["x_packed"], ptrs["row_scale"], ptrs["y"])
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.ws.device)
+
+    # ------------------------------------------------------------------ phases (all launch-only)
+    def phase_route(self, x: torch.Tensor, attention_mask=None, router_logits=None):
+        m, ws = self.m, self.ws
+        hook = m.stage_hook or (lambda _n: None)
+        hook("start")
+        wg = m.gate.weight.detach()
+        self._x = x
+        self._route = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
+        hook("router")
+        ops.plan(ws)                     # local counts + block prefix sums (+ local aux loss)
+        self._aux = ws.aux_loss.clone().reshape(())
+        vec = torch.cat([ws.counts.clone(), torch.tensor([ws.T], dtype=torch.int32, device=ws.device)])
+        hook("plan")
+        return vec
+
+    def phase_dispatch(self, all_counts: torch.Tensor):
+        lib = _lib.load()
+        ws, d = self.ws, self.m.dims
+        hook = self.m.stage_hook or (lambda _n: None)
+        cfg = d.c_config(ws.dtype)
+        st = torch.cuda.current_stream().cuda_stream
+        self._all_counts = all_counts.contiguous()
+        _lib.check(lib.dcmoe_ep_plan(self._all_counts.data_ptr(), self.rank, self.world, ws.T, ws.row_capacity, cfg,
+                                     ws.plan.data_ptr(), ws.ep_meta.data_ptr(), st), "dcmoe_ep_plan")
+        hook("ep_plan")
+        _, _, mask, gw = self._route
+        xp, rs, _y = self._peer
+        _lib.check(lib.dcmoe_ep_dispatch(self._x.data_ptr(), mask.data_ptr(), gw.data_ptr(), ws.T, ws.row_capacity, cfg,
+                                         ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
+                                         ws.slot_of.data_ptr(), st), "dcmoe_ep_dispatch")
+        hook("ep_dispatch")
+
+    def phase_ffn(self):
+        lib = _lib.load()
+        ws = self.ws
+        hook = self.m.stage_hook or (lambda _n: None)
+        cfg = self.local_dims.c_config(ws.dtype)
+        impl = self.m.ffn_impl if self.m.ffn_impl is not None else (0 if ws.dtype == torch.bfloat16 else 1)
+        st = torch.cuda.current_stream().cuda_stream
+        for phase, name in ((1, "ffn_gemm1"), (2, "ffn_gemm2")):
+            _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
+                                             self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, cfg,
+                                             ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl, phase, st),
+                       "dcmoe_grouped_ffn")
+            hook(name)
+
+    def phase_combine(self, out: torch.Tensor):
+        lib = _lib.load()
+        ws, d = self.ws, self.m.dims
+        hook = self.m.stage_hook or (lambda _n: None)
+        _xp, _rs, y = self._peer
+        _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr(), y, ws.slot_of.data_ptr(), ws.T, d.c_config(ws.dtype), self.world,
+                                        out.data_ptr(), torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
+        hook("ep_combine")
+
+    # ------------------------------------------------------------------ distributed forward
+    @torch.no_grad()
+    def __call__(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
+        import torch.distributed as dist
+
+        if aux_balance_weight is not None:
+            raise NotImplementedError("aux_balance_weight is training-only")
+        B, S, H = hidden_states.shape
+        T = B * S
+        x = hidden_states.reshape(T, H)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        self.pack_local_weights()
+        ws = self.ensure_workspace(T, x.dtype, x.device, ipc=True)
+        if self._peer is None:
+            self._exchange_handles()
+        hook = self.m.stage_hook or (lambda _n: None)
+        vec = self.phase_route(x, attention_mask, router_logits)
+        all_counts = torch.empty((self.world, vec.numel()), dtype=torch.int32, device=x.device)
+        dist.all_gather_into_tensor(all_counts, vec, group=self.group)          # also the "buffers are free" barrier
+        hook("allgather_counts")
+        self.phase_dispatch(all_counts)
+        dist.all_reduce(self._flag, group=self.group)                            # every rank's rows have landed
+        hook("barrier_dispatch")
+        self.phase_ffn()
+        dist.all_reduce(self._flag, group=self.group)                            # every owner's y is complete
+        hook("barrier_ffn")
+        out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
+        self.phase_combine(out.view(T, H))
+        logits, top_k, mask, gw = self._route
+        return out, logits, top_k, mask, gw, self._aux
+
+
+class LocalRanks:
+    """R virtual ranks in one process on one GPU: the same kernels and call order as the distributed forward,
+    with the collectives replaced by torch ops on the ranks' tensors.  Test / debugging aid."""
+
+    def __init__(self, module: DCMoE, world: int):
+        self.world = world
+        self.ranks = [ExpertParallelDCMoE(module, group=None, rank=r, world=world) for r in range(world)]
+
+    @torch.no_grad()
+    def forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
+        R = self.world
+        shapes = [x.shape for x in xs]
+        flat = [x.reshape(-1, x.shape[-1]).contiguous() for x in xs]
+        T_global = sum(f.shape[0] for f in flat)
+        for r, ep in enumerate(self.ranks):
+            ep.pack_local_weights()
+            ep.ensure_workspace(flat[r].shape[0], flat[r].dtype, flat[r].device, ipc=False, T_global=T_global)
+        for ep in self.ranks:
+            ep.set_peers([q.ws.x_packed.data_ptr() for q in self.ranks], [q.ws.row_scale.data_ptr() for q in self.ranks],
+                         [q.ws.y.data_ptr() for q in self.ranks])
+        vecs = [ep.phase_route(flat[r], None if attention_masks is None else attention_masks[r]) for r, ep in enumerate(self.ranks)]
+        all_counts = torch.stack(vecs).contiguous()
+        for ep in self.ranks:
+            ep.phase_dispatch(all_counts)
+        for ep in self.ranks:
+            ep.phase_ffn()
+        outs = []
+        for r, ep in enumerate(self.ranks):
+            out = torch.empty_like(flat[r])
+            ep.phase_combine(out)
+            logits, top_k, mask, gw = ep._route
+            outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
+        self.all_counts = all_counts
+        return outs

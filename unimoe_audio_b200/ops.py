@@ -63,7 +63,8 @@ class Workspace:
     rows, the FFN intermediates and the permutation maps.  Sized for the worst case (every token routed
     to every real expert) unless ``row_capacity`` is given."""
 
-    def __init__(self, dims: LayerDims, dtype: torch.dtype, T: int, device, row_capacity: int = 0):
+    def __init__(self, dims: LayerDims, dtype: torch.dtype, T: int, device, row_capacity: int = 0,
+                 alloc_peer_visible: bool = True):
         self.dims, self.dtype, self.T, self.device = dims, dtype, T, torch.device(device)
         self.sizes, self.layout = query_sizes(dims, dtype, T, row_capacity)
         self.row_capacity = int(self.sizes.row_capacity)
@@ -71,12 +72,15 @@ class Workspace:
         dev = self.device
         self.plan = torch.zeros(int(self.sizes.plan_bytes), dtype=torch.uint8, device=dev)
         H, Id = dims.hidden_size, dims.dynamic_intermediate_size
-        self.x_packed = torch.empty((max(self.row_capacity - self.t_pad, 1), H), dtype=dtype, device=dev)
+        self.shapes = {"x_packed": (max(self.row_capacity - self.t_pad, 1), H), "y": (self.row_capacity, H),
+                       "row_scale": (self.row_capacity, 2)}
         self.h = torch.empty((self.row_capacity, Id), dtype=dtype, device=dev)
-        self.y = torch.empty((self.row_capacity, H), dtype=dtype, device=dev)
+        if alloc_peer_visible:   # expert parallelism allocates these three with dcmoe_ipc_alloc instead
+            self.x_packed = torch.empty(self.shapes["x_packed"], dtype=dtype, device=dev)
+            self.y = torch.empty(self.shapes["y"], dtype=dtype, device=dev)
+            self.row_scale = torch.zeros(self.shapes["row_scale"], dtype=torch.float32, device=dev)
         self.slot_of = torch.empty((max(T, 1), dims.n_real), dtype=torch.int32, device=dev)
         self.row_token = torch.full((self.row_capacity,), -1, dtype=torch.int32, device=dev)
-        self.row_scale = torch.zeros((self.row_capacity, 2), dtype=torch.float32, device=dev)
 
     # typed views into the plan buffer (device tensors; reading them on the host synchronises)
     def _view(self, off: int, n: int, dt: torch.dtype) -> torch.Tensor:
