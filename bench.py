@@ -52,53 +52,61 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (a thread polling every
+    20 ms: NVML queries take driver locks, so polling faster -- or spawning nvidia-smi -- stalls kernel launches)."""
 
     def __init__(self, gpu_index: int):
-        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+        self.gpu_index, self.samples, self._stop, self.thread, self.err = gpu_index, [], False, None, None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.err = str(exc)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                pw = 0.0
+                self.samples.append((time.perf_counter(), float(sm), int(rs), pw))
+            except Exception as exc:  # noqa: BLE001
+                self.err = str(exc)
+                return
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [c.strip() for c in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        load = sorted(sm)[len(sm) // 2:] if sm else []
-        return dict(sm_mhz=statistics.median(load) if load else None, sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+        self._stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        if self.err is not None and not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[f"nvml unavailable: {self.err}"])
+        nv = self.nv
+        inside = [s for s in self.samples if self.t_begin is not None and self.t_begin <= s[0] <= (self.t_end or 1e30)]
+        use = inside or self.samples
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in names.items() if any(s[2] & bit for s in use))
+        sm = [s[1] for s in use]
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_min_mhz=min(sm) if sm else None, sm_max_mhz=self.sm_max,
+                    reasons=reasons, samples=len(use),
+                    samples_in_timed_region=len(inside))
 
 
 def dist_env():
@@ -218,15 +226,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         layer(xs[i % n_rot], None, None)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     m.stage_hook = hook
+    if rank == 0:
+        sampler.mark_begin()
     step_ev = []
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         stage_events.append([])
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,7 +245,10 @@ def run_ours(args):
         out = layer(xs[(args.warmup + i) % n_rot], None, None)
         e.record()
         step_ev.append((s, e))
+    host_ms_per_step = (time.perf_counter() - host_t0) * 1e3 / args.steps   # enqueue time only (no sync)
     barrier()
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     m.stage_hook = None
     total_ms = step_ev[0][0].elapsed_time(step_ev[-1][1])     # K steps back to back, first start -> last end
@@ -250,7 +264,7 @@ def run_ours(args):
     for evs in stage_events:
         for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
             stages.setdefault(n1, []).append(e0.elapsed_time(e1))
-    stage_ms = {k: sum(v) / len(v) for k, v in stages.items()}
+    stage_ms = {k: statistics.median(v) for k, v in stages.items()}   # median: robust to a host hiccup in one step
 
     # routed rows of the last step (A = sum_t r_t) -> algorithmic FLOPs of the grouped GEMMs
     ws = m.last_workspace
@@ -287,41 +301,36 @@ def run_ours(args):
         roofline["gemm2"] = {"achieved": n_rows_local * FLOP_PER_ROW_GEMM2 / (stage_ms["ffn_gemm2"] * 1e-3) / 1e12,
                              "unit": "TFLOP/s", "ms": stage_ms["ffn_gemm2"]}
 
-    # ---- e2e: public module call with pinned host buffers, copies inside the timed region ----
+    # ---- e2e: the public host-buffer API (unimoe_audio_b200.host.HostPipeline): every step copies its input
+    # from pinned host memory and its whole 6-tuple back to pinned host memory inside the timed region; the
+    # copies of neighbouring steps overlap the compute of the current one (3 streams, PCIe full duplex) ----
+    from unimoe_audio_b200.host import HostPipeline
     x_host = [x.cpu().pin_memory() for x in xs[:2]]
-    x_dev = torch.empty_like(xs[0])
-    out_host = None
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def e2e_step(i):
-        nonlocal out_host
-        x_dev.copy_(x_host[i % 2], non_blocking=True)
-        o = layer(x_dev, None, None)
-        if out_host is None:
-            out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in o]
-        for h, t in zip(out_host, o):
-            h.copy_(t, non_blocking=True)
-        return o
-
-    for i in range(2):
-        e2e_step(i)
+    pipe = HostPipeline(layer, depth=2, device=dev)
+    e2e_steps = max(6, min(args.steps, 40))
+    for i in range(3):
+        pipe.submit(x_host[i % 2])
+        pipe.result()
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     s.record()
     for i in range(e2e_steps):
-        o = e2e_step(i)
+        if len(pipe.pending) == pipe.depth:
+            o = pipe.result()
+        pipe.submit(x_host[i % 2])
+    while pipe.pending:
+        o = pipe.result()                       # host tensors of the last step are complete here
+    wall_ms = (time.perf_counter() - t0) * 1e3
     e.record()
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(s.elapsed_time(e), 0.0)
+    e2e_ms = max(s.elapsed_time(e), wall_ms)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = t.item()
     e2e_value = T * world * e2e_steps / (e2e_ms * 1e-3)
-    h2d = x_dev.numel() * x_dev.element_size()
-    d2h = sum(t.numel() * t.element_size() for t in o)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -341,10 +350,14 @@ def run_ours(args):
                        "ffn_rows_rank0": A, "weights": "random N(0, 0.02^2)", "top_p": 0.7},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "wall_ms_per_step": wall_ms / e2e_steps,
+                    "api": "unimoe_audio_b200.host.HostPipeline(depth=2): pinned host in/out, copies overlapped across steps"},
             "gpu_launches": KERNELS_PER_STEP * args.steps if world == 1 else None,
             "roofline": roofline,
             "stage_ms": stage_ms,
+            "host_enqueue_ms_per_step": host_ms_per_step,
+            "step_ms_first3": [a.elapsed_time(b) for a, b in step_ev[:3]],
+            "step_ms_last3": [a.elapsed_time(b) for a, b in step_ev[-3:]],
             "cpu_baseline": cpu_baseline,
             "peaks": peaks,
         }
@@ -358,7 +371,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -22,6 +22,8 @@
 //     floating point follows the canonical arithmetic of oracle/route_oracle.c (explicit
 //     __f*_rn intrinsics, never contracted), so dynamic_top_k, expert_mask AND global_weight
 //     are bit-identical to the oracle for identical logits.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dcmoe {
@@ -101,91 +103,145 @@ __device__ __forceinline__ float row_sum8_lanes(float d, int n) {
 struct RouteConsts {
     float thr_p, thr_eps, plus_eps, finfo_min;
     int n_dyn, E;
+    int always_softmax;   // debug: evaluate the mixer softmax even when it is provably 1 (DCMOE_ROUTER_ALWAYS_SOFTMAX=1)
 };
+
+// exp of the canonical arithmetic for dtype D
+template <bool BF16>
+__device__ __forceinline__ float exp_D(float x) {
+    return BF16 ? exp_cr(x) : exp_sleef_u10(x);
+}
+
+// sequential sum of lanes [0, n) of a 16-lane group, in lane order (ATen softmax order)
+__device__ __forceinline__ float seq_sum_lanes(float e, const int n) {
+    float s = __shfl_sync(kFull, e, 0, 16);
+#pragma unroll
+    for (int i = 1; i < kMaxDyn; ++i) {
+        if (i < n) s = __fadd_rn(s, __shfl_sync(kFull, e, i, 16));
+    }
+    return s;
+}
+
+// descending rank of v among lanes [0, n) of the 16-lane group, ties broken by lower lane first
+__device__ __forceinline__ int rank_desc_lanes(float v, int j, const int n) {
+    int rank = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxDyn; ++i) {
+        if (i < n) {
+            const float vi = __shfl_sync(kFull, v, i, 16);
+            rank += (vi > v) || (vi == v && i < j);
+        }
+    }
+    return rank;
+}
+
+// inverse of a permutation held one entry per lane: lane r gets the lane whose rank is r
+__device__ __forceinline__ int inverse_perm_lanes(int rank, int j, const int n) {
+    int src = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxDyn; ++i) {
+        if (i < n) {
+            const int ri = __shfl_sync(kFull, rank, i, 16);
+            if (ri == j) src = i;
+        }
+    }
+    return src;
+}
 
 // Route one token per 16-lane group.  l = logit of lane j (D-representable fp32), am = padding mask.
 // NDYN / NE > 0 fix the expert counts at compile time (the reference config: 9 dynamic + 2 shared), which
 // trims every shuffle loop to its real length; 0 = read them from rc.
+//
+// The reference's iterative arg-max loop (core.py:103-147) selects experts in the order of the logits sorted
+// descending with ties to the lower index, so one rank computation replaces the k arg-max reductions; the
+// softmax inside iteration `it` has max == the it-th largest logit, e = 1 for it and exactly 0 for every
+// dropped / already selected entry, i.e. it is exactly 1 unless another remaining logit lies within 2 % of
+// the current maximum ("near tie").  Only near ties (about 3 % of iterations) evaluate it.
 template <bool BF16, int NDYN, int NE>
 __device__ __forceinline__ void route_token(float l, int j, int half, int am, const RouteConsts& rc, int& raw_out,
                                             int& mask_out, float& gw_out, float& ga_out) {
     const int n_dyn = NDYN ? NDYN : rc.n_dyn, E = NE ? NE : rc.E;
     const float ninf = __int_as_float(0xff800000);
     const bool dyn = j < n_dyn;
+    const unsigned half_mask = 0xffffu << (half * 16);
+    // ---- selection order: logits descending, ties -> lower index (torch.max first occurrence) ----
+    const int rank_l = rank_desc_lanes(dyn ? l : ninf, j, n_dyn);
+    const int src_l = inverse_perm_lanes(rank_l, j, n_dyn);          // lane r: index of the r-th largest logit
+    const float sorted_l = __shfl_sync(kFull, l, src_l, 16);         // lane r: r-th largest logit
+    const float top1 = __shfl_sync(kFull, sorted_l, 0, 16);
     // ---- Top-P count (core.py:162-166) ----
-    float p = softmax_lanes<BF16>(dyn ? l : ninf, j, n_dyn);
-    int rank = 0;
+    float e = dyn ? exp_D<BF16>(__fsub_rn(l, top1)) : 0.0f;
+    float inv = __fdiv_rn(1.0f, seq_sum_lanes(e, n_dyn));
+    const float p = rnd<BF16>(__fmul_rn(e, inv));
+    // sorted probabilities: a correctly rounded exp is monotone, so in bf16 the order of p is the order of l
+    // (ties give equal values, and only the sorted VALUES matter); fp32 ranks p itself.
+    int src_p = src_l;
+    if (!BF16) src_p = inverse_perm_lanes(rank_desc_lanes(dyn ? p : ninf, j, n_dyn), j, n_dyn);
+    const float sorted_p = __shfl_sync(kFull, p, src_p, 16);         // lane r: r-th largest probability
+    float run = 0.0f;                                                // lane r ends with prefix c_r
 #pragma unroll
     for (int i = 0; i < kMaxDyn; ++i) {
         if (i < n_dyn) {
-            float pi = __shfl_sync(kFull, p, i, 16);
-            rank += (pi > p) || (pi == p && i < j);
+            const float v = __shfl_sync(kFull, sorted_p, i, 16);
+            if (i <= j) run = __fadd_rn(run, v);
         }
     }
-    int raw = 1;
-    float run = 0.0f;
-#pragma unroll
-    for (int r = 0; r < kMaxDyn; ++r) {
-        if (r < n_dyn) {
-            unsigned b = __ballot_sync(kFull, dyn && rank == r);
-            b = (b >> (half * 16)) & 0xffffu;
-            int src = __ffs(b) - 1;
-            float val = __shfl_sync(kFull, p, src & 15, 16);
-            run = __fadd_rn(run, val);
-            float c = rnd<BF16>(run);
-            raw += !(c >= rc.thr_p);
-        }
-    }
+    const bool below = dyn && !(rnd<BF16>(run) >= rc.thr_p);
+    const int raw = 1 + __popc(__ballot_sync(kFull, below) & half_mask);
     raw_out = raw;
     const int k = raw <= n_dyn ? raw : 0;
-    int kmax = max(k, __shfl_xor_sync(kFull, k, 16));
+    const int kmax = max(k, __shfl_xor_sync(kFull, k, 16));
     // ---- mixer (core.py:103-147, eval branch) ----
-    float rem = dyn ? l : ninf;
-    float rw = 0.0f;
-    int sel = 0;
+    float rw = (dyn && rank_l < k) ? 1.0f : 0.0f;
+    bool had_tie = false;
     for (int it = 0; it < kmax; ++it) {
-        float bv = rem;
-        int bi = j;
-#pragma unroll
-        for (int off = 8; off >= 1; off >>= 1) {
-            float ov = __shfl_xor_sync(kFull, bv, off, 16);
-            int oi = __shfl_xor_sync(kFull, bi, off, 16);
-            if (ov > bv || (ov == bv && oi < bi)) {
-                bv = ov;
-                bi = oi;
-            }
-        }
-        const float thr = bv;
+        const float thr = __shfl_sync(kFull, sorted_l, it, 16);
         const float fac = fmaxf(fabsf(l), fabsf(thr));
         const float diff = rnd<BF16>(__fsub_rn(thr, l));
         const float ratio = rnd<BF16>(__fdiv_rn(diff, fac));
         const bool drop = ratio > rc.thr_eps;
-        const float g = (dyn && !drop) ? rem : ninf;
-        // The softmax of core.py:118 has max == thr, so e[bi] = exp(0) = 1 exactly and every dropped or
-        // already selected entry contributes exp(-inf) = 0 exactly: unless another remaining logit is within
-        // 2 % of thr (a "near tie", ~3 % of iterations) the sum is exactly 1 and the multiplier exactly 1.
-        // Skip the exp/sum/div then (warp-uniform test); the result is bit-identical to the full softmax.
-        const bool near_tie = (g != ninf) && (j != bi) && (it < k);
-        float sm = 1.0f;
-        if (__any_sync(kFull, near_tie)) sm = softmax_lanes<BF16>(g, j, n_dyn);
-        if (it < k && j == bi) {
-            rw = sm;
-            sel = 1;
-            rem = ninf;
+        const bool remaining = dyn && rank_l >= it;
+        const bool near_tie = remaining && rank_l != it && !drop && it < k;
+        const unsigned ties = __ballot_sync(kFull, near_tie);
+        if (ties != 0u || rc.always_softmax) {                        // warp-uniform
+            const float sm = softmax_lanes<BF16>((remaining && !drop) ? l : ninf, j, n_dyn);
+            if (it < k && rank_l == it) rw = sm;
+            had_tie |= (ties & half_mask) != 0u;
         }
     }
+    const int sel = (dyn && rank_l < k) ? 1 : 0;
     // ---- normalise (core.py:284) ----
-    const float rs = rnd<BF16>(row_sum8_lanes(dyn ? rw : 0.0f, n_dyn));
-    const float den = rnd<BF16>(__fadd_rn(rs, rc.plus_eps));
+    float rsum = (float)k;                                            // k exact ones when no near tie occurred
+    if (__any_sync(kFull, had_tie) || rc.always_softmax) {
+        const float full = row_sum8_lanes(dyn ? rw : 0.0f, n_dyn);
+        if (had_tie || rc.always_softmax) rsum = full;
+    }
+    const float den = rnd<BF16>(__fadd_rn(rnd<BF16>(rsum), rc.plus_eps));
     rw = rnd<BF16>(__fdiv_rn(rw, den));
     // ---- padding mask, shared experts always on (core.py:286-291) ----
-    int mk = dyn ? sel * am : (j < E ? 1 : 0);
-    // ---- aux-loss softmax (core.py:370-373) ----
-    ga_out = softmax_lanes<BF16>(dyn ? (mk ? l : rc.finfo_min) : ninf, j, n_dyn);
-    // ---- global weights (core.py:188-192) ----
-    const float G = softmax_lanes<BF16>((j < E && mk) ? l : ninf, j, E);
-    const float dsum = rnd<BF16>(row_sum8_lanes(dyn ? G : 0.0f, n_dyn));
-    gw_out = dyn ? rnd<BF16>(__fmul_rn(rw, dsum)) : G;
+    const int mk = dyn ? sel * am : (j < E ? 1 : 0);
+    const bool any_sel = (k > 0) && (am != 0);
+    // ---- aux-loss softmax (core.py:370-373): selected logits, finfo.min elsewhere ----
+    {
+        const float m = any_sel ? top1 : rc.finfo_min;
+        // exp(finfo.min - m) is exactly 0 for any real m and exp(0) = 1 when everything is masked
+        const float ea = dyn ? (mk ? exp_D<BF16>(__fsub_rn(l, m)) : (any_sel ? 0.0f : 1.0f)) : 0.0f;
+        const float ia = __fdiv_rn(1.0f, seq_sum_lanes(ea, n_dyn));
+        ga_out = rnd<BF16>(__fmul_rn(ea, ia));
+    }
+    // ---- global weights (core.py:188-192): 11-way softmax over selected + shared ----
+    {
+        float m = any_sel ? top1 : ninf;
+#pragma unroll
+        for (int i = 0; i < kMaxDyn; ++i) {
+            if (i >= n_dyn && i < E) m = fmaxf(m, __shfl_sync(kFull, l, i, 16));
+        }
+        const float eg = (j < E && mk) ? exp_D<BF16>(__fsub_rn(l, m)) : 0.0f;
+        const float ig = __fdiv_rn(1.0f, seq_sum_lanes(eg, E));
+        const float G = rnd<BF16>(__fmul_rn(eg, ig));
+        const float dsum = rnd<BF16>(row_sum8_lanes(dyn ? G : 0.0f, n_dyn));
+        gw_out = dyn ? rnd<BF16>(__fmul_rn(rw, dsum)) : G;
+    }
     mask_out = mk;
 }
 
@@ -364,6 +420,10 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     rc.thr_eps = r((float)(2.0 * cfg->jitter_eps));
     rc.plus_eps = r(1e-6f);
     rc.finfo_min = bf16 ? -3.3895313892515355e38f : -3.4028234663852886e38f;
+    {
+        const char* dbg = getenv("DCMOE_ROUTER_ALWAYS_SOFTMAX");
+        rc.always_softmax = (dbg && dbg[0] == '1') ? 1 : 0;
+    }
     const int64_t n_blocks = ceil_div(T, kRouterBlock);
     dim3 grid((unsigned)n_blocks), block(128);
 #define DCMOE_LAUNCH_ROUTER(BF, ND, NE_)                                                                              \

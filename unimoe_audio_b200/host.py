@@ -1,0 +1,83 @@
+"""Host-buffer front end of the DCMoE layer: pinned host tensors in, pinned host tensors out.
+
+``DCMoE.forward`` takes device tensors (that is what the decoder layer hands it, model.py:241).  A caller that
+owns HOST activations (the end-to-end measurement of bench.py, or a CPU-resident pipeline stage) uses
+``HostPipeline``: every step copies its input host->device, runs the layer and copies the whole 6-tuple
+device->host, with the three phases of consecutive steps overlapped on three CUDA streams
+(H2D of step i+1 and D2H of step i-1 run while step i computes; PCIe is full duplex).  Nothing is cached:
+each step's bytes cross the bus inside the pipeline.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Callable, Deque, List, Optional, Tuple
+
+import torch
+
+
+class HostPipeline:
+    def __init__(self, layer: Callable, depth: int = 2, device: Optional[torch.device] = None):
+        self.layer = layer
+        self.depth = depth
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.x_dev: List[Optional[torch.Tensor]] = [None] * depth
+        self.out_host: List[Optional[List[torch.Tensor]]] = [None] * depth
+        self.ev_h2d = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_compute = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(depth)]
+        self.pending: Deque[int] = deque()
+        self.step = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def submit(self, x_host: torch.Tensor, attention_mask=None):
+        """Enqueue one step.  ``x_host`` must be pinned.  Returns nothing; call ``result()`` in order."""
+        if not x_host.is_pinned():
+            raise ValueError("HostPipeline needs pinned host memory for asynchronous copies")
+        slot = self.step % self.depth
+        if len(self.pending) == self.depth:
+            raise RuntimeError("pipeline full: call result() before submitting more steps")
+        cur = torch.cuda.current_stream(self.device)
+        if self.x_dev[slot] is None or self.x_dev[slot].shape != x_host.shape or self.x_dev[slot].dtype != x_host.dtype:
+            self.x_dev[slot] = torch.empty(x_host.shape, dtype=x_host.dtype, device=self.device)
+        # H2D on the copy-in stream, after the compute that last read this slot
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_compute[slot])
+            self.x_dev[slot].copy_(x_host, non_blocking=True)
+            self.ev_h2d[slot].record(self.s_in)
+        # compute on the caller's stream
+        cur.wait_event(self.ev_h2d[slot])
+        out = self.layer(self.x_dev[slot], attention_mask, None)
+        self.ev_compute[slot].record(cur)
+        # D2H on the copy-out stream
+        if self.out_host[slot] is None or any(h.shape != t.shape for h, t in zip(self.out_host[slot], out)):
+            self.out_host[slot] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in out]
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_compute[slot])
+            for h, t in zip(self.out_host[slot], out):
+                t.record_stream(self.s_out)
+                h.copy_(t, non_blocking=True)
+            self.ev_d2h[slot].record(self.s_out)
+        self.h2d_bytes = x_host.numel() * x_host.element_size()
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in out)
+        self.pending.append(slot)
+        self.step += 1
+
+    def result(self) -> Tuple[torch.Tensor, ...]:
+        """Block until the oldest submitted step's outputs are in host memory and return them (the host
+        tensors are reused ``depth`` steps later)."""
+        slot = self.pending.popleft()
+        self.ev_d2h[slot].synchronize()
+        return tuple(self.out_host[slot])
+
+    def run(self, xs_host) -> List[Tuple[torch.Tensor, ...]]:
+        outs = []
+        for x in xs_host:
+            if len(self.pending) == self.depth:
+                outs.append(tuple(t.clone() for t in self.result()))
+            self.submit(x)
+        while self.pending:
+            outs.append(tuple(t.clone() for t in self.result()))
+        return outs
