@@ -275,3 +275,35 @@ def test_layer_config2_size_properties_and_sliced_parity(dev):
         sl = slice(s0, s0 + 256)
         ref = O.forward(xf[sl].reshape(1, 256, 2048), W, None, logits=logits[sl].cpu())
         _check_layer(final.reshape(T, 2048)[sl], ref.final_hidden_states.reshape(256, 2048), dt)
+
+
+def test_bf16_layer_is_at_least_as_accurate_as_the_reference_arithmetic(dev):
+    """Both the reference's bf16 path and ours are rounded versions of the same real-valued layer.  Against an fp32
+    evaluation (same bf16 weights, same routing) our error must not exceed the reference arithmetic's own error."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=4)
+    x = torch.randn(1, 384, 2048, generator=torch.Generator().manual_seed(21)).to(dt)
+    out = m(x.to(dev), None, None)
+    torch.cuda.synchronize()
+    logits = out[1].cpu()
+    ref_bf16 = O.forward(x, W, None, logits=logits).final_hidden_states.float().reshape(-1, 2048)
+    # fp32 "truth": identical routing decisions and weights (taken from the bf16 run), fp32 arithmetic in the FFNs
+    W32 = {k: v.float() for k, v in W.items()}
+    gw = out[4].cpu().float()
+    mask = out[3].cpu()
+    xf = x.float().reshape(-1, 2048)
+    truth = torch.zeros_like(xf)
+    for e in range(8):
+        idx = torch.nonzero(mask[:, e], as_tuple=True)[0]
+        if idx.numel():
+            y = O._ffn(xf[idx], W32[O.ROUTED.format(e=e, proj="gate_proj")], W32[O.ROUTED.format(e=e, proj="up_proj")],
+                       W32[O.ROUTED.format(e=e, proj="down_proj")])
+            truth.index_add_(0, idx, gw[idx, e, None] * y)
+    for e in range(2):
+        y = O._ffn(xf, W32[O.SHARED.format(e=e, proj="gate_proj")], W32[O.SHARED.format(e=e, proj="up_proj")],
+                   W32[O.SHARED.format(e=e, proj="down_proj")])
+        truth += gw[:, 9 + e, None] * y
+    ours = out[0].float().cpu().reshape(-1, 2048)
+    err_ours = ((ours - truth).norm() / truth.norm()).item()
+    err_ref = ((ref_bf16 - truth).norm() / truth.norm()).item()
+    assert err_ours <= 1.05 * err_ref + 1e-4, (err_ours, err_ref)

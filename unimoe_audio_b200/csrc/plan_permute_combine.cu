@@ -33,17 +33,19 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp < n_real) {
-        // exclusive scan of expert `warp` over token blocks: 8 consecutive blocks per lane, 256 per step
+        // exclusive scan of expert `warp` over token blocks: 16 consecutive blocks per lane, 512 per step
         const int e = warp;
         int carry = 0;
-        for (int base = 0; base < n_blocks; base += 256) {
-            int v[8], sum = 0;
+        constexpr int PER = 16;
+        for (int base = 0; base < n_blocks; base += 32 * PER) {
+            int v[PER], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int b = base + lane * 8 + i;
+            for (int i = 0; i < PER; ++i) {
+                const int b = base + lane * PER + i;
                 v[i] = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
-                sum += v[i];
             }
+#pragma unroll
+            for (int i = 0; i < PER; ++i) sum += v[i];
             int incl = sum;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
@@ -52,8 +54,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
             }
             int run = carry + incl - sum;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int b = base + lane * 8 + i;
+            for (int i = 0; i < PER; ++i) {
+                const int b = base + lane * PER + i;
                 if (b < n_blocks) pv.block_offsets[(int64_t)b * n_real + e] = run;
                 run += v[i];
             }
@@ -69,9 +71,21 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         const int j = warp - 16;
         double ps = 0.0;
         long long ts = 0;
-        for (int b = lane; b < n_blocks; b += 32) {
-            ps += (double)pv.block_probs[(int64_t)b * n_dyn + j];
-            ts += pv.block_counts[(int64_t)b * n_dyn + j];
+        constexpr int U = 16;                                      // independent loads in flight per lane
+        for (int b0 = lane; b0 < n_blocks; b0 += 32 * U) {
+            float pr[U];
+            int ct[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int b = b0 + 32 * u;
+                pr[u] = b < n_blocks ? pv.block_probs[(int64_t)b * n_dyn + j] : 0.0f;
+                ct[u] = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                          // fixed order: u ascending
+                ps += (double)pr[u];
+                ts += ct[u];
+            }
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {

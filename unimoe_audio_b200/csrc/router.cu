@@ -170,7 +170,10 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
     const float sorted_l = __shfl_sync(kFull, l, src_l, 16);         // lane r: r-th largest logit
     const float top1 = __shfl_sync(kFull, sorted_l, 0, 16);
     // ---- Top-P count (core.py:162-166) ----
-    float e = dyn ? exp_D<BF16>(__fsub_rn(l, top1)) : 0.0f;
+    // e_j = exp(l_j - top1) is evaluated once for every lane j < E: the aux softmax (max = top1 whenever an
+    // expert is selected) and, when no shared logit exceeds top1, the 11-way softmax reuse the same values.
+    const float e_all = (j < E) ? exp_D<BF16>(__fsub_rn(l, top1)) : 0.0f;
+    const float e = dyn ? e_all : 0.0f;
     float inv = __fdiv_rn(1.0f, seq_sum_lanes(e, n_dyn));
     const float p = rnd<BF16>(__fmul_rn(e, inv));
     // sorted probabilities: a correctly rounded exp is monotone, so in bf16 the order of p is the order of l
@@ -198,8 +201,14 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
         const float thr = __shfl_sync(kFull, sorted_l, it, 16);
         const float fac = fmaxf(fabsf(l), fabsf(thr));
         const float diff = rnd<BF16>(__fsub_rn(thr, l));
-        const float ratio = rnd<BF16>(__fdiv_rn(diff, fac));
-        const bool drop = ratio > rc.thr_eps;
+        // drop <=> rnd(diff / fac) > t, t = 2*eps.  Outside [0.75 t, 1.5 t] * fac the outcome is certain (the
+        // rounding of the quotient moves it by < 0.4 %), so the IEEE division only runs for borderline lanes.
+        bool drop = diff > rc.thr_eps * fac;
+        const bool borderline = !(diff < 0.75f * rc.thr_eps * fac) && !(diff > 1.5f * rc.thr_eps * fac);  // also NaN, fac == 0
+        if (__any_sync(kFull, borderline && dyn)) {
+            const float ratio = rnd<BF16>(__fdiv_rn(diff, fac));
+            if (borderline) drop = ratio > rc.thr_eps;
+        }
         const bool remaining = dyn && rank_l >= it;
         const bool near_tie = remaining && rank_l != it && !drop && it < k;
         const unsigned ties = __ballot_sync(kFull, near_tie);
@@ -223,20 +232,26 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
     const bool any_sel = (k > 0) && (am != 0);
     // ---- aux-loss softmax (core.py:370-373): selected logits, finfo.min elsewhere ----
     {
-        const float m = any_sel ? top1 : rc.finfo_min;
-        // exp(finfo.min - m) is exactly 0 for any real m and exp(0) = 1 when everything is masked
-        const float ea = dyn ? (mk ? exp_D<BF16>(__fsub_rn(l, m)) : (any_sel ? 0.0f : 1.0f)) : 0.0f;
+        // max = top1 if anything is selected (exp(finfo.min - top1) is exactly 0), else every entry is
+        // finfo.min and exp(0) = 1
+        const float ea = dyn ? (any_sel ? (mk ? e_all : 0.0f) : 1.0f) : 0.0f;
         const float ia = __fdiv_rn(1.0f, seq_sum_lanes(ea, n_dyn));
         ga_out = rnd<BF16>(__fmul_rn(ea, ia));
     }
     // ---- global weights (core.py:188-192): 11-way softmax over selected + shared ----
     {
-        float m = any_sel ? top1 : ninf;
+        float ms = ninf;                                              // max of the shared logits
 #pragma unroll
         for (int i = 0; i < kMaxDyn; ++i) {
-            if (i >= n_dyn && i < E) m = fmaxf(m, __shfl_sync(kFull, l, i, 16));
+            if (i >= n_dyn && i < E) ms = fmaxf(ms, __shfl_sync(kFull, l, i, 16));
         }
-        const float eg = (j < E && mk) ? exp_D<BF16>(__fsub_rn(l, m)) : 0.0f;
+        const bool reuse = any_sel && top1 >= ms;                     // softmax max == top1: same exp arguments
+        float eg = (j < E && mk) ? e_all : 0.0f;
+        if (!__all_sync(kFull, reuse)) {                              // warp-uniform
+            const float m = any_sel ? fmaxf(top1, ms) : ms;
+            const float eg2 = (j < E && mk) ? exp_D<BF16>(__fsub_rn(l, m)) : 0.0f;
+            if (!reuse) eg = eg2;
+        }
         const float ig = __fdiv_rn(1.0f, seq_sum_lanes(eg, E));
         const float G = rnd<BF16>(__fmul_rn(eg, ig));
         const float dsum = rnd<BF16>(row_sum8_lanes(dyn ? G : 0.0f, n_dyn));
@@ -404,6 +419,135 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised persistent router (bf16): the gate projection is HBM bound, the routing maths is
+// latency / issue bound.  In the one-CTA-per-block kernel above every CTA of the (single) wave streams x first
+// and routes afterwards, so the two phases of the whole grid run back to back.  Here each CTA keeps 8 "gate"
+// warps streaming x for successive token blocks (two groups of 4 warps, K split four ways, 8 x 16 B per lane in
+// flight) and 8 "routing" warps consuming the logits through a 4-stage smem ring, so HBM traffic and the
+// shuffle/exp chains overlap for the whole kernel.  Named barriers (bar.arrive / bar.sync) hand the stages over.
+constexpr int kWsStages = 4;
+constexpr int kWsThreads = 512;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int NDYN, int NE>
+__global__ void __launch_bounds__(kWsThreads, 2)
+router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wg,
+                 const int32_t* __restrict__ attn_mask, int64_t T, int H, int n_blocks, RouteConsts rc,
+                 __nv_bfloat16* __restrict__ logits_out, int64_t* __restrict__ top_k,
+                 int32_t* __restrict__ expert_mask, __nv_bfloat16* __restrict__ gw_out,
+                 int32_t* __restrict__ block_counts, float* __restrict__ block_probs) {
+    __shared__ float red[kWsStages][4][kRouterBlock][16];
+    __shared__ int s_cnt[2][kRouterBlock][kMaxDyn];
+    __shared__ float s_prob[2][kRouterBlock][kMaxDyn];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = NE ? NE : rc.E;
+    const int n_dyn = NDYN ? NDYN : rc.n_dyn;
+    constexpr int kFullCount = 128 + 256;   // one gate group + the routing warps
+    // barrier ids: 1..4 full[s], 5..8 empty[s], 9 routing-internal
+    if (warp < 8) {
+        // ================= gate warps =================
+        const int grp = warp >> 2, wq = warp & 3;
+        const int Kq = H >> 2, k0 = wq * Kq;
+        const int g = lane >> 2, tq = lane & 3;
+        const bool wv0 = g < E, wv1 = g + 8 < E;
+        const __nv_bfloat16* w0 = wg + (int64_t)(wv0 ? g : 0) * H + k0 + tq * 8;
+        const __nv_bfloat16* w1 = wg + (int64_t)(wv1 ? g + 8 : 0) * H + k0 + tq * 8;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        const int steps = Kq >> 5;
+        int it = grp;
+        for (int blk = blockIdx.x + grp * gridDim.x; blk < n_blocks; blk += 2 * gridDim.x, it += 2) {
+            const int st = it & (kWsStages - 1);
+            const int64_t tok0 = (int64_t)blk * kRouterBlock;
+            const int64_t r0 = tok0 + g, r1 = r0 + 8;
+            const bool v0 = r0 < T, v1 = r1 < T;
+            const __nv_bfloat16* xr0 = x + (v0 ? r0 : 0) * (int64_t)H + k0 + tq * 8;
+            const __nv_bfloat16* xr1 = x + (v1 ? r1 : 0) * (int64_t)H + k0 + tq * 8;
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int s0 = 0; s0 < steps; s0 += 4) {
+                uint4 a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[u] = v0 ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;
+                    b[u] = v1 ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint4 q0 = wv0 ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
+                    uint4 q1 = wv1 ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
+                    mma_bf16_16816(c0, a[u].x, b[u].x, a[u].y, b[u].y, q0.x, q0.y);
+                    mma_bf16_16816(c0, a[u].z, b[u].z, a[u].w, b[u].w, q0.z, q0.w);
+                    mma_bf16_16816(c1, a[u].x, b[u].x, a[u].y, b[u].y, q1.x, q1.y);
+                    mma_bf16_16816(c1, a[u].z, b[u].z, a[u].w, b[u].w, q1.z, q1.w);
+                }
+            }
+            if (it >= kWsStages) named_bar_sync(5 + st, kFullCount);   // routing warps released this stage
+            red[st][wq][g][2 * tq] = c0[0];
+            red[st][wq][g][2 * tq + 1] = c0[1];
+            red[st][wq][g + 8][2 * tq] = c0[2];
+            red[st][wq][g + 8][2 * tq + 1] = c0[3];
+            red[st][wq][g][8 + 2 * tq] = c1[0];
+            red[st][wq][g][8 + 2 * tq + 1] = c1[1];
+            red[st][wq][g + 8][8 + 2 * tq] = c1[2];
+            red[st][wq][g + 8][8 + 2 * tq + 1] = c1[3];
+            __threadfence_block();
+            named_bar_arrive(1 + st, kFullCount);
+        }
+    } else {
+        // ================= routing warps =================
+        const int rw_ = warp - 8;
+        const int half = lane >> 4, j = lane & 15;
+        const int rtid = tid - 256;
+        int it = 0;
+        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const int st = it & (kWsStages - 1);
+            const int64_t tok0 = (int64_t)blk * kRouterBlock;
+            const int tl = rw_ * 2 + half;
+            const int64_t t = tok0 + tl;
+            const bool valid = t < T;
+            named_bar_sync(1 + st, kFullCount);
+            float l = 0.0f;
+            if (j < E) {
+                l = __fadd_rn(__fadd_rn(__fadd_rn(red[st][0][tl][j], red[st][1][tl][j]), red[st][2][tl][j]), red[st][3][tl][j]);
+                l = bf16_round(l);
+            }
+            // hand the stage back only if the gate group will write it again
+            if ((int64_t)blk + (int64_t)kWsStages * gridDim.x < n_blocks) named_bar_arrive(5 + st, kFullCount);
+            const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
+            int raw, mk;
+            float gw, ga;
+            route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            if (valid && j < E) {
+                logits_out[t * E + j] = __float2bfloat16_rn(l);
+                gw_out[t * E + j] = __float2bfloat16_rn(gw);
+                expert_mask[t * E + j] = mk;
+                if (j == 0) top_k[t] = raw;
+            }
+            const int sb = it & 1;
+            s_cnt[sb][tl][j] = (valid && j < n_dyn) ? mk : 0;
+            s_prob[sb][tl][j] = (valid && j < n_dyn) ? ga : 0.0f;
+            named_bar_sync(9, 256);
+            if (rtid < n_dyn) {
+                int cnt = 0;
+                float pr = 0.0f;
+#pragma unroll
+                for (int r = 0; r < kRouterBlock; ++r) {
+                    cnt += s_cnt[sb][r][rtid];
+                    pr = __fadd_rn(pr, s_prob[sb][r][rtid]);
+                }
+                block_counts[(int64_t)blk * n_dyn + rtid] = cnt;
+                block_probs[(int64_t)blk * n_dyn + rtid] = pr;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
@@ -431,6 +575,27 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
                                                            logits_out, top_k, expert_mask, global_weight,            \
                                                            block_counts, block_probs)
     const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
+    static int ws_mode = -1;
+    if (ws_mode < 0) {
+        const char* env = getenv("DCMOE_ROUTER_WS");      // debug switch: 0 = one CTA per block kernel
+        ws_mode = (env && env[0] == '0') ? 0 : 1;
+    }
+    if (bf16 && logits_in == nullptr && ws_mode == 1) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t want = 2 * (int64_t)sms;
+        dim3 g2((unsigned)(n_blocks < want ? n_blocks : want)), b2(kWsThreads);
+        if (ref_shape)
+            router_ws_kernel<9, 11><<<g2, b2, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask, T,
+                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
+                (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        else
+            router_ws_kernel<0, 0><<<g2, b2, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask, T,
+                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
+                (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        return check_cuda(cudaGetLastError(), "router_ws_kernel launch");
+    }
     if (bf16) {
         if (ref_shape) DCMOE_LAUNCH_ROUTER(true, 9, 11); else DCMOE_LAUNCH_ROUTER(true, 0, 0);
     } else {

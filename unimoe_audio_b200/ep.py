@@ -195,7 +195,9 @@ class ExpertParallelDCMoE:
         hook("router")
         ops.plan(ws)                     # local counts + block prefix sums (+ local aux loss)
         self._aux = ws.aux_loss.clone().reshape(())
-        vec = torch.cat([ws.counts.clone(), torch.tensor([ws.T], dtype=torch.int32, device=ws.device)])
+        if getattr(ws, "_t_const", None) is None:      # cached: a fresh torch.tensor(..., device=) is a blocking H2D copy
+            ws._t_const = torch.tensor([ws.T], dtype=torch.int32, device=ws.device)
+        vec = torch.cat([ws.counts, ws._t_const])
         hook("plan")
         return vec
 

@@ -67,6 +67,7 @@ class Workspace:
                  alloc_peer_visible: bool = True):
         self.dims, self.dtype, self.T, self.device = dims, dtype, T, torch.device(device)
         self.sizes, self.layout = query_sizes(dims, dtype, T, row_capacity)
+        self.cfg = dims.c_config(dtype)          # cached ctypes struct (built once per workspace)
         self.row_capacity = int(self.sizes.row_capacity)
         self.t_pad = int(self.sizes.t_pad)
         dev = self.device
@@ -126,7 +127,7 @@ def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Worksp
     if logits_in is not None:
         if logits_in.shape != (T, E) or logits_in.dtype != dt or not logits_in.is_contiguous():
             raise ValueError("logits_in must be a contiguous [T, E] tensor of the layer dtype")
-    cfg = dims.c_config(dt)
+    cfg = ws.cfg
     _lib.check(lib.dcmoe_router(_ptr(x), _ptr(w_gate), _ptr(logits_in), _ptr(am), T, cfg, _ptr(logits), _ptr(top_k),
                                 _ptr(mask), _ptr(gw), _ptr(ws.plan), _stream()), "dcmoe_router")
     return logits, top_k, mask, gw
@@ -134,26 +135,26 @@ def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Worksp
 
 def plan(ws: Workspace):
     lib = _lib.load()
-    _lib.check(lib.dcmoe_plan(ws.T, ws.row_capacity, ws.dims.c_config(ws.dtype), _ptr(ws.plan), _stream()), "dcmoe_plan")
+    _lib.check(lib.dcmoe_plan(ws.T, ws.row_capacity, ws.cfg, _ptr(ws.plan), _stream()), "dcmoe_plan")
 
 
 def permute(x: torch.Tensor, expert_mask: torch.Tensor, global_weight: torch.Tensor, ws: Workspace):
     lib = _lib.load()
     _lib.check(lib.dcmoe_permute(_ptr(x), _ptr(expert_mask), _ptr(global_weight), ws.T, ws.row_capacity,
-                                 ws.dims.c_config(ws.dtype), _ptr(ws.plan), _ptr(ws.x_packed), _ptr(ws.slot_of),
+                                 ws.cfg, _ptr(ws.plan), _ptr(ws.x_packed), _ptr(ws.slot_of),
                                  _ptr(ws.row_token), _ptr(ws.row_scale), _stream()), "dcmoe_permute")
 
 
 def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Workspace, impl: int = 0, phase: int = 0):
     lib = _lib.load()
     _lib.check(lib.dcmoe_grouped_ffn(_ptr(x), _ptr(ws.x_packed), _ptr(w13), _ptr(w2), _ptr(ws.row_scale), ws.T,
-                                     ws.row_capacity, ws.dims.c_config(ws.dtype), _ptr(ws.plan), _ptr(ws.h), _ptr(ws.y),
+                                     ws.row_capacity, ws.cfg, _ptr(ws.plan), _ptr(ws.h), _ptr(ws.y),
                                      impl, phase, _stream()), "dcmoe_grouped_ffn")
 
 
 def combine(ws: Workspace, out: torch.Tensor):
     lib = _lib.load()
-    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.dims.c_config(ws.dtype), _ptr(out), _stream()),
+    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(out), _stream()),
                "dcmoe_combine")
 
 
