@@ -154,8 +154,11 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *   y            [row_capacity, H] D      already weighted expert outputs
  *   impl         0 = tcgen05/TMEM/TMA grouped GEMM (bf16 only), 1 = CUDA-core fp32-accumulate GEMM
  *                (the fp32 layer path; also usable with bf16 for cross-checking)
- *   phase        0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
- *                put CUDA events between the two launches
+ *   phase        low 4 bits: 0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
+ *                put CUDA events between the two launches.  Bits 4-5 select the tile group (tcgen05 only):
+ *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism
+ *                runs the shared experts while the dispatch is still in flight.  Bits 8-19: cap on the number of
+ *                persistent CTAs (0 = one per SM), to leave SMs to concurrently running dispatch / combine kernels
  */
 int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                       int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,
@@ -202,20 +205,26 @@ int dcmoe_ipc_close(void* ptr);
 
 /* all_counts: device int32 [world][n_real + 1] (per-rank routed rows per global expert, then the rank's T).
  * Writes this rank's row-space layout (seg_base, counts of the LOCAL experts, tile table) into `plan` and the
- * destinations of this rank's rows into ep_meta (device int32 [DCMOE_EP_META_INTS]). */
+ * destinations of this rank's rows into ep_meta (device int32 [DCMOE_EP_META_INTS]); also writes the shared-expert
+ * scales of the local rows (row_scale_local[t] = global_weight[t, n_dyn..]) so the shared experts can start early. */
 int dcmoe_ep_plan(const int32_t* all_counts, int rank, int world, int64_t T, int64_t row_capacity,
-                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, void* stream);
+                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, const void* global_weight,
+                  float* row_scale_local, void* stream);
 
 /* peer_x_packed / peer_row_scale: HOST arrays of `world` device pointers (entry `rank` = this rank's own
- * buffers).  slot_of [T, n_real] receives the row-space row ON THE OWNER of (token, expert), or -1. */
+ * buffers).  slot_of [T, n_real] receives the row-space row ON THE OWNER of (token, expert), or -1.
+ * max_ctas > 0 caps the grid (the kernels loop), for running them next to a persistent GEMM. */
 int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T,
                       int64_t row_capacity, const dcmoe_config* cfg, const void* plan, const int32_t* ep_meta,
                       int rank, int world, void* const* peer_x_packed, float* const* peer_row_scale, int32_t* slot_of,
-                      void* stream);
+                      int max_ctas, void* stream);
 
-/* peer_y: HOST array of `world` device pointers to the ranks' y buffers.  out [T, H] D. */
+/* peer_y: HOST array of `world` device pointers to the ranks' y buffers.  out [T, H] D.
+ * mode 0: whole combine.  mode 1: partial[T, H] (fp32) = sum of the routed rows only (can run while the shared
+ * experts' GEMM-2 is still computing); mode 2: out = D(partial + shared row).  0 and 1+2 give bitwise equal outputs. */
 int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32_t* slot_of, int64_t T,
-                     const dcmoe_config* cfg, int world, void* out, void* stream);
+                     const dcmoe_config* cfg, int world, int mode, float* partial, void* out, int max_ctas,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,13 +25,14 @@ def setup():
     return m, W, dev, dt
 
 
+@pytest.mark.parametrize("split", [False, True], ids=["serial", "overlap-schedule"])
 @pytest.mark.parametrize("world,tokens", [(2, [300, 300]), (4, [257, 16, 1, 130]), (8, [64] * 8), (2, [1000, 24])])
-def test_local_ranks_match_single_gpu(setup, world, tokens):
+def test_local_ranks_match_single_gpu(setup, world, tokens, split):
     from unimoe_audio_b200.ep import LocalRanks, ep_layout
     m, W, dev, dt = setup
     gen = torch.Generator().manual_seed(sum(tokens) + world)
     xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
-    lr = LocalRanks(m, world)
+    lr = LocalRanks(m, world, split=split)
     outs = lr.forward(xs)
     torch.cuda.synchronize()
     x_all = torch.cat(xs, dim=1)

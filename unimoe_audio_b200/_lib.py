@@ -60,11 +60,12 @@ SIGNATURES = {
     "dcmoe_ipc_export": (c_int, [c_void_p, c_void_p]),
     "dcmoe_ipc_import": (c_int, [c_void_p, POINTER(c_void_p)]),
     "dcmoe_ipc_close": (c_int, [c_void_p]),
-    "dcmoe_ep_plan": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p]),
+    "dcmoe_ep_plan": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
     "dcmoe_ep_dispatch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
-                                  c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p]),
-    "dcmoe_ep_combine": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_int64, POINTER(DcmoeConfig), c_int, c_void_p,
-                                 c_void_p]),
+                                  c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
+    "dcmoe_ep_combine": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_int64, POINTER(DcmoeConfig), c_int, c_int,
+                                 c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 

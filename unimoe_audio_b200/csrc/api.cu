@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace dcmoe {
@@ -58,6 +60,45 @@ int validate_config(const dcmoe_config* cfg) {
     return DCMOE_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+        set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(err));
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols], box [box_rows, 64 cols], 128B swizzle
+int make_tensor_map_bf16(void* map_, const void* base, int64_t rows, int64_t cols, int box_rows) {
+    CUtensorMap* map = static_cast<CUtensorMap*>(map_);
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return DCMOE_ERR_CUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d base=%p", (int)r, (long long)rows,
+                  (long long)cols, box_rows, base);
+        return DCMOE_ERR_CUDA;
+    }
+    return DCMOE_OK;
+}
+
+
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_hint, dcmoe_sizes* sz,
@@ -98,9 +139,9 @@ int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, vo
 int launch_pack(const void*, const void*, const void*, int, int, const dcmoe_config*, void*, void*, cudaStream_t);
 int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv);
 int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
-                    const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
+                    const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
-                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
+                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 
 static int require_device() {
     int n = 0;
@@ -198,6 +239,11 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
 int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                       int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,
                       int impl, int phase, void* stream) {
+    // phase: low 4 bits = 0 both GEMMs / 1 GEMM-1 / 2 GEMM-2; bits 4-5 = group selection (0 all tiles,
+    // 1 shared-expert tiles only, 2 routed tiles only)
+    const int group_sel = (phase >> 4) & 3;
+    const int max_ctas = (phase >> 8) & 0xfff;   // bits 8-19: cap on the persistent grid (0 = one CTA per SM)
+    phase &= 15;
     DCMOE_PROLOGUE(T)
     if (T > 0 && (!x || !x_packed || !w13 || !w2 || !row_scale || !plan || !h || !y)) {
         set_error("dcmoe_grouped_ffn: NULL pointer argument");
@@ -207,10 +253,11 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
     if (impl == 0) return launch_ffn_tcgen05(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
-                                             phase, (cudaStream_t)stream);
+                                             phase, group_sel, max_ctas, (cudaStream_t)stream);
     if (impl == 1) {
         if (sz.max_mtiles > 65535) { set_error("CUDA-core FFN: too many row tiles (%lld)", (long long)sz.max_mtiles); return DCMOE_ERR_INVALID; }
-        return launch_ffn_simt(x, x_packed, w13, w2, row_scale, T, cfg, sz, pv, h, y, phase, (cudaStream_t)stream);
+        if (group_sel != 0) { set_error("CUDA-core FFN does not support tile-group selection"); return DCMOE_ERR_INVALID; }
+        return launch_ffn_simt(x, x_packed, w13, w2, row_scale, T, cfg, sz, pv, h, y, phase, group_sel, (cudaStream_t)stream);
     }
     set_error("dcmoe_grouped_ffn: unknown impl %d", impl);
     return DCMOE_ERR_INVALID;

@@ -17,6 +17,9 @@ constexpr int kMaxDyn = 16;                       // n_real + n_null upper bound
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t err, const char* what);
 int validate_config(const dcmoe_config* cfg);
+// 2-D bf16 row-major tensor [rows, cols] -> CUtensorMap (void*: CUtensorMap*) with box [box_rows, 64 cols] and
+// 128B swizzle (api.cu)
+int make_tensor_map_bf16(void* map, const void* base, int64_t rows, int64_t cols, int box_rows);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

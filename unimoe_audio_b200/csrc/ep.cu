@@ -110,18 +110,36 @@ __global__ void __launch_bounds__(256) ep_plan_kernel(const int32_t* __restrict_
     }
 }
 
+// shared-expert row scales (gw[t, n_dyn], gw[t, n_dyn + 1]) of the local rows [0, T): written here, before the
+// dispatch, so that the shared experts' GEMM-1 can run while the dispatch is still in flight
+template <int ESIZE>
+__global__ void ep_shared_scale_kernel(const char* __restrict__ gw, int64_t T, int n_dyn, int n_fix,
+                                       float* __restrict__ row_scale) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int E = n_dyn + n_fix;
+    auto load_gw = [&](int j) -> float {
+        if (ESIZE == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gw)[t * E + j]);
+        return reinterpret_cast<const float*>(gw)[t * E + j];
+    };
+    row_scale[2 * t] = load_gw(n_dyn);
+    row_scale[2 * t + 1] = n_fix > 1 ? load_gw(n_dyn + 1) : 0.0f;
+}
+
 template <int ESIZE>
 __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict__ x, const int32_t* __restrict__ mask,
                                                           const char* __restrict__ gw, int64_t T, int H, int n_real,
                                                           int n_dyn, int n_fix, int n_loc, int rank,
                                                           const int32_t* __restrict__ block_offsets,
                                                           const int32_t* __restrict__ ep_meta, EpPeers peers,
-                                                          int32_t* __restrict__ slot_of) {
+                                                          int32_t* __restrict__ slot_of, int n_blocks) {
     __shared__ int s_m[kRouterBlock][kMaxDyn];
     __shared__ int s_slot[kRouterBlock][kMaxDyn];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = n_dyn + n_fix;
-    const int64_t tok0 = (int64_t)blockIdx.x * kRouterBlock;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {   // grid may be capped (comm under compute)
+    __syncthreads();
+    const int64_t tok0 = (int64_t)blk * kRouterBlock;
     auto load_gw = [&](int64_t t, int j) -> float {
         if (ESIZE == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gw)[t * E + j]);
         return reinterpret_cast<const float*>(gw)[t * E + j];
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict
         for (int q = 0; q < tl; ++q) rk += s_m[q][e];
         int slot = -1;
         if (s_m[tl][e]) {
-            slot = ep_meta[e] + block_offsets[(int64_t)blockIdx.x * n_real + e] + rk;   // row on the owner
+            slot = ep_meta[e] + block_offsets[(int64_t)blk * n_real + e] + rk;   // row on the owner
             const float w = load_gw(t, e);
             float* sc = peers.row_scale[e / n_loc];
             sc[2 * (int64_t)slot] = w;
@@ -148,14 +166,7 @@ __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict
         s_slot[tl][e] = slot;
         if (t < T) slot_of[t * n_real + e] = slot;
     }
-    if (tid < kRouterBlock) {
-        const int64_t t = tok0 + tid;
-        if (t < T) {
-            float* sc = peers.row_scale[rank];
-            sc[2 * t] = load_gw(t, n_dyn);
-            sc[2 * t + 1] = n_fix > 1 ? load_gw(t, n_dyn + 1) : 0.0f;
-        }
-    }
+    (void)rank;
     __syncthreads();
     const int n_vec = H * ESIZE / 16;
     for (int q = 0; q < kRouterBlock / 4; ++q) {
@@ -186,77 +197,157 @@ __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict
             }
         }
     }
+    }  // block loop
 }
 
-template <bool BF16>
-__global__ void __launch_bounds__(256) ep_combine_kernel(const char* __restrict__ y_local, EpPeers peers,
-                                                         const int32_t* __restrict__ slot_of, int64_t T, int H,
-                                                         int n_real, int n_loc, char* __restrict__ out) {
+// MODE 0: out = D(sum of routed rows (expert order) + shared row)          -- the whole combine
+// MODE 1: partial[t] = fp32 sum of routed rows                              -- overlappable with the shared GEMM-2
+// MODE 2: out = D(partial[t] + shared row)
+// MODE 0 and MODE 1 + MODE 2 perform the same fp32 additions in the same order (bitwise equal outputs).
+template <bool BF16, int MODE>
+__global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restrict__ y_local, EpPeers peers,
+                                                            const int32_t* __restrict__ slot_of, int64_t T, int H,
+                                                            int n_real, int n_loc, float* __restrict__ partial,
+                                                            char* __restrict__ out) {
     constexpr int ESIZE = BF16 ? 2 : 4;
     constexpr int PER = 16 / ESIZE;
+    constexpr int U = 4;             // 128-bit vectors per lane per pass (x 2 source rows in flight)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
-    if (t >= T) return;
-    const int my_slot = lane < n_real ? slot_of[t * n_real + lane] : -1;
     const int n_vec = H * ESIZE / 16;
     const int64_t row_bytes = (int64_t)H * ESIZE;
-    auto accumulate = [&](float (&acc)[8][PER], const uint4 (&v)[8], bool init) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float f[8];
-            if (BF16) {
-                f[0] = bf16lo(v[u].x); f[1] = bf16hi(v[u].x); f[2] = bf16lo(v[u].y); f[3] = bf16hi(v[u].y);
-                f[4] = bf16lo(v[u].z); f[5] = bf16hi(v[u].z); f[6] = bf16lo(v[u].w); f[7] = bf16hi(v[u].w);
-            } else {
-                f[0] = __uint_as_float(v[u].x); f[1] = __uint_as_float(v[u].y);
-                f[2] = __uint_as_float(v[u].z); f[3] = __uint_as_float(v[u].w);
-            }
-#pragma unroll
-            for (int i = 0; i < PER; ++i) acc[u][i] = init ? f[i] : acc[u][i] + f[i];
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < T; t += (int64_t)gridDim.x * 8) {   // grid may be capped
+    // compact source list, in accumulation order: lane i < n_src holds the base pointer of source row i
+    // (selected routed rows in expert order, then the shared row)
+    const char* my_src = nullptr;
+    int n_src = 0;
+    {
+        int slot = -1;
+        if (MODE != 2 && lane < n_real) slot = slot_of[t * n_real + lane];
+        const unsigned sel = __ballot_sync(kFull, slot >= 0);
+        const char* p = slot >= 0 ? peers.y[lane / n_loc] + (int64_t)slot * row_bytes : nullptr;   // local or NVLink peer
+        const int pos = __popc(sel & ((1u << lane) - 1u));
+        n_src = __popc(sel);
+        // scatter lane -> position pos: every destination lane i pulls from the i-th set bit of sel
+        int srcl = 0;
+        {
+            unsigned m = sel;
+            for (int i = 0; i < lane && m; ++i) m &= m - 1;          // drop the `lane` lowest set bits
+            srcl = m ? __ffs(m) - 1 : 0;
         }
-    };
-    for (int c0 = 0; c0 < n_vec; c0 += 256) {
-        float acc[8][PER];
-        uint4 v[8];
-        const uint4* src = reinterpret_cast<const uint4*>(y_local + t * row_bytes);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 32 + lane;
-            v[u] = c < n_vec ? ld_nc_v4(src + c) : make_uint4(0, 0, 0, 0);
-        }
-        accumulate(acc, v, true);
-        for (int e = 0; e < n_real; ++e) {
-            const int slot = __shfl_sync(kFull, my_slot, e);
-            if (slot < 0) continue;
-            const uint4* s2 = reinterpret_cast<const uint4*>(peers.y[e / n_loc] + (int64_t)slot * row_bytes);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c0 + u * 32 + lane;
-                v[u] = c < n_vec ? ld_nc_v4(s2 + c) : make_uint4(0, 0, 0, 0);   // local HBM or NVLink peer read
-            }
-            accumulate(acc, v, false);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + t * row_bytes);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 32 + lane;
-            if (c >= n_vec) continue;
-            uint4 o;
-            if (BF16) {
-                o.x = pack_bf16(acc[u][0], acc[u][1]);
-                o.y = pack_bf16(acc[u][2 % PER], acc[u][3 % PER]);
-                o.z = pack_bf16(acc[u][4 % PER], acc[u][5 % PER]);
-                o.w = pack_bf16(acc[u][6 % PER], acc[u][7 % PER]);
-            } else {
-                o.x = __float_as_uint(acc[u][0]); o.y = __float_as_uint(acc[u][1]);
-                o.z = __float_as_uint(acc[u][2]); o.w = __float_as_uint(acc[u][3]);
-            }
-            st_na_v4(dst + c, o);
+        (void)pos;
+        const unsigned long long pv = __shfl_sync(kFull, (unsigned long long)p, srcl);
+        my_src = lane < n_src ? (const char*)pv : nullptr;
+        if (MODE != 1) {                                             // the shared row comes last
+            if (lane == n_src) my_src = y_local + t * row_bytes;
+            n_src += 1;
         }
     }
+    auto add = [&](float (&acc)[U][PER], const uint4 (&v)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (BF16) {
+                acc[u][0] += bf16lo(v[u].x); acc[u][1] += bf16hi(v[u].x);
+                acc[u][2 % PER] += bf16lo(v[u].y); acc[u][3 % PER] += bf16hi(v[u].y);
+                acc[u][4 % PER] += bf16lo(v[u].z); acc[u][5 % PER] += bf16hi(v[u].z);
+                acc[u][6 % PER] += bf16lo(v[u].w); acc[u][7 % PER] += bf16hi(v[u].w);
+            } else {
+                acc[u][0] += __uint_as_float(v[u].x); acc[u][1] += __uint_as_float(v[u].y);
+                acc[u][2] += __uint_as_float(v[u].z); acc[u][3] += __uint_as_float(v[u].w);
+            }
+        }
+    };
+    for (int c0 = 0; c0 < n_vec; c0 += 32 * U) {
+        float acc[U][PER];
+        if (MODE == 2) {
+            // resume from the fp32 partial sums: element k of vector c lives at partial[t*H + c*PER + k]
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < PER / 4; ++q) {
+                    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < n_vec) f = *reinterpret_cast<const float4*>(partial + t * (int64_t)H + (int64_t)c * PER + 4 * q);
+                    acc[u][4 * q] = f.x; acc[u][4 * q + 1] = f.y; acc[u][4 * q + 2] = f.z; acc[u][4 * q + 3] = f.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < PER; ++i) acc[u][i] = 0.0f;
+        }
+        // two source rows (2 x U x 128-bit per lane) in flight; accumulation stays in list order
+        for (int i = 0; i < n_src; i += 2) {
+            const uint4* s0 = reinterpret_cast<const uint4*>((const char*)__shfl_sync(kFull, (unsigned long long)my_src, i));
+            const bool two = i + 1 < n_src;
+            const uint4* s1 = reinterpret_cast<const uint4*>((const char*)__shfl_sync(kFull, (unsigned long long)my_src, two ? i + 1 : i));
+            uint4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * 32 + lane;
+                v0[u] = c < n_vec ? ld_nc_v4(s0 + c) : make_uint4(0, 0, 0, 0);
+            }
+            if (two) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    v1[u] = c < n_vec ? ld_nc_v4(s1 + c) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            add(acc, v0);
+            if (two) add(acc, v1);
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * 32 + lane;
+                if (c >= n_vec) continue;
+#pragma unroll
+                for (int q = 0; q < PER / 4; ++q)
+                    *reinterpret_cast<float4*>(partial + t * (int64_t)H + (int64_t)c * PER + 4 * q) =
+                        make_float4(acc[u][4 * q], acc[u][4 * q + 1], acc[u][4 * q + 2], acc[u][4 * q + 3]);
+            }
+        } else {
+            uint4* dst = reinterpret_cast<uint4*>(out + t * row_bytes);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int c = c0 + u * 32 + lane;
+                if (c >= n_vec) continue;
+                uint4 o;
+                if (BF16) {
+                    o.x = pack_bf16(acc[u][0], acc[u][1]);
+                    o.y = pack_bf16(acc[u][2 % PER], acc[u][3 % PER]);
+                    o.z = pack_bf16(acc[u][4 % PER], acc[u][5 % PER]);
+                    o.w = pack_bf16(acc[u][6 % PER], acc[u][7 % PER]);
+                } else {
+                    o.x = __float_as_uint(acc[u][0]); o.y = __float_as_uint(acc[u][1]);
+                    o.z = __float_as_uint(acc[u][2]); o.w = __float_as_uint(acc[u][3]);
+                }
+                st_na_v4(dst + c, o);
+            }
+        }
+    }
+    }  // token loop
 }
 
 }  // namespace
+
+// single-GPU combine = the expert-parallel combine with one rank (peers.y[0] = y)
+int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out,
+                   cudaStream_t stream) {
+    if (T == 0) return DCMOE_OK;
+    EpPeers peers{};
+    peers.y[0] = (const char*)y;
+    dim3 grid((unsigned)ceil_div(T, 8)), block(256);
+    if (cfg->dtype == DCMOE_BF16)
+        ep_combine_kernel<true, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
+                                                               cfg->n_real, cfg->n_real, nullptr, (char*)out);
+    else
+        ep_combine_kernel<false, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
+                                                                cfg->n_real, cfg->n_real, nullptr, (char*)out);
+    return check_cuda(cudaGetLastError(), "combine kernel launch");
+}
+
 }  // namespace dcmoe
 
 using namespace dcmoe;
@@ -291,11 +382,12 @@ int dcmoe_ipc_import(const uint8_t* handle64, void** ptr) {
 int dcmoe_ipc_close(void* ptr) { return check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle"); }
 
 int dcmoe_ep_plan(const int32_t* all_counts, int rank, int world, int64_t T, int64_t row_capacity,
-                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, void* stream) {
+                  const dcmoe_config* cfg, void* plan, int32_t* ep_meta, const void* global_weight,
+                  float* row_scale_local, void* stream) {
     int rc = validate_config(cfg);
     if (rc) return rc;
-    if (!all_counts || !plan || !ep_meta || world < 1 || world > kMaxRanks || rank < 0 || rank >= world ||
-        cfg->n_real % world != 0) {
+    if (!all_counts || !plan || !ep_meta || !global_weight || !row_scale_local || world < 1 || world > kMaxRanks ||
+        rank < 0 || rank >= world || cfg->n_real % world != 0) {
         set_error("dcmoe_ep_plan: bad arguments (world=%d rank=%d n_real=%d)", world, rank, cfg->n_real);
         return DCMOE_ERR_INVALID;
     }
@@ -303,13 +395,23 @@ int dcmoe_ep_plan(const int32_t* all_counts, int rank, int world, int64_t T, int
     if ((rc = ep_plan_view(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
     ep_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(all_counts, rank, world, cfg->n_real, cfg->n_real / world, T,
                                                         (int)sz.max_mtiles, pv, ep_meta);
-    return check_cuda(cudaGetLastError(), "ep_plan_kernel launch");
+    if ((rc = check_cuda(cudaGetLastError(), "ep_plan_kernel launch"))) return rc;
+    if (T > 0) {
+        const int n_dyn = cfg->n_real + cfg->n_null;
+        dim3 grid((unsigned)ceil_div(T, 256)), block(256);
+        if (cfg->dtype == DCMOE_BF16)
+            ep_shared_scale_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)global_weight, T, n_dyn, cfg->n_fix, row_scale_local);
+        else
+            ep_shared_scale_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)global_weight, T, n_dyn, cfg->n_fix, row_scale_local);
+        rc = check_cuda(cudaGetLastError(), "ep_shared_scale_kernel launch");
+    }
+    return rc;
 }
 
 int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T,
                       int64_t row_capacity, const dcmoe_config* cfg, const void* plan, const int32_t* ep_meta,
                       int rank, int world, void* const* peer_x_packed, float* const* peer_row_scale, int32_t* slot_of,
-                      void* stream) {
+                      int max_ctas, void* stream) {
     int rc = validate_config(cfg);
     if (rc) return rc;
     if (T == 0) return DCMOE_OK;
@@ -323,34 +425,42 @@ int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* glo
     EpPeers peers{};
     for (int r = 0; r < world; ++r) { peers.x_packed[r] = (char*)peer_x_packed[r]; peers.row_scale[r] = peer_row_scale[r]; }
     const int n_dyn = cfg->n_real + cfg->n_null;
-    dim3 grid((unsigned)sz.n_blocks), block(128);
+    int64_t nb = sz.n_blocks;
+    if (max_ctas > 0 && nb > max_ctas) nb = max_ctas;
+    dim3 grid((unsigned)nb), block(128);
     if (cfg->dtype == DCMOE_BF16)
         ep_dispatch_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
-            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of);
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks);
     else
         ep_dispatch_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
-            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of);
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks);
     return check_cuda(cudaGetLastError(), "ep_dispatch_kernel launch");
 }
 
 int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32_t* slot_of, int64_t T,
-                     const dcmoe_config* cfg, int world, void* out, void* stream) {
+                     const dcmoe_config* cfg, int world, int mode, float* partial, void* out, int max_ctas,
+                     void* stream) {
     int rc = validate_config(cfg);
     if (rc) return rc;
     if (T == 0) return DCMOE_OK;
-    if (!y_local || !peer_y || !slot_of || !out || world < 1 || world > kMaxRanks || cfg->n_real % world != 0) {
+    if (!y_local || !peer_y || !slot_of || world < 1 || world > kMaxRanks || cfg->n_real % world != 0 || mode < 0 ||
+        mode > 2 || (mode != 1 && !out) || (mode != 0 && !partial)) {
         set_error("dcmoe_ep_combine: bad arguments");
         return DCMOE_ERR_INVALID;
     }
     EpPeers peers{};
     for (int r = 0; r < world; ++r) peers.y[r] = (const char*)peer_y[r];
-    dim3 grid((unsigned)ceil_div(T, 8)), block(256);
-    if (cfg->dtype == DCMOE_BF16)
-        ep_combine_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,
-            cfg->hidden_size, cfg->n_real, cfg->n_real / world, (char*)out);
-    else
-        ep_combine_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,
-            cfg->hidden_size, cfg->n_real, cfg->n_real / world, (char*)out);
+    int64_t nb = ceil_div(T, 8);
+    if (max_ctas > 0 && nb > max_ctas) nb = max_ctas;
+    dim3 grid((unsigned)nb), block(256);
+    const bool bf16 = cfg->dtype == DCMOE_BF16;
+#define DCMOE_EP_COMBINE(BF, MODE_)                                                                                   \
+    ep_combine_kernel<BF, MODE_><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,  \
+        cfg->hidden_size, cfg->n_real, cfg->n_real / world, partial, (char*)out)
+    if (mode == 0) { if (bf16) DCMOE_EP_COMBINE(true, 0); else DCMOE_EP_COMBINE(false, 0); }
+    else if (mode == 1) { if (bf16) DCMOE_EP_COMBINE(true, 1); else DCMOE_EP_COMBINE(false, 1); }
+    else { if (bf16) DCMOE_EP_COMBINE(true, 2); else DCMOE_EP_COMBINE(false, 2); }
+#undef DCMOE_EP_COMBINE
     return check_cuda(cudaGetLastError(), "ep_combine_kernel launch");
 }
 

@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const void* __restrict__
 
 int launch_ffn_simt(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                     int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv, void* h, void* y,
-                    int phase, cudaStream_t stream) {
+                    int phase, int group_sel, cudaStream_t stream) {
+    (void)group_sel;  // the CUDA-core path always processes every tile
     if (T == 0) return DCMOE_OK;
     const int H = cfg->hidden_size, Id = cfg->dynamic_intermediate_size;
     dim3 block(256);

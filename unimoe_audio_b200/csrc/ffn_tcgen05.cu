@@ -27,6 +27,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcmoe {
 namespace {
@@ -36,108 +37,13 @@ constexpr int A_BYTES = BM * BK * 2;             // 16 KB
 constexpr int B_BYTES = BN * BK * 2;             // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
 constexpr int EPI_SLAB = 32 * 128;               // 32 rows x 64 bf16
-constexpr int EPI_BYTES = 4 * 2 * EPI_SLAB;      // 4 warps x 2 buffers
+constexpr int EPI_BUFS = 1;                      // slabs per epilogue warp (1: leaves ~18 KB of smem per SM for a
+                                                 // co-resident dispatch / combine CTA when expert parallelism overlaps them)
+constexpr int EPI_BYTES = 4 * EPI_BUFS * EPI_SLAB;
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 256;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-// Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 50000000u) {
-            printf("dcmoe ffn_tcgen05: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(src), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 columns of fp32: thread i <- TMEM lane (base + i), columns [col, col + 32)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled smem operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 |
 // SBO = 1024 B (8 rows x 128 B) | version 1 | layout SWIZZLE_128B
@@ -167,6 +73,8 @@ struct GemmParams {
     const dcmoe_mtile* mtiles;
     const int32_t* n_mtiles;
     const float* row_scale;
+    int m_begin;        // first m-tile of this launch
+    int m_end;          // one past the last m-tile; < 0: read *n_mtiles
 };
 
 // ------------------------------------------------------------------ kernel
@@ -213,14 +121,15 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int total_tiles = (*p.n_mtiles) * p.n_tiles;
+    const int m_end = p.m_end >= 0 ? min(p.m_end, *p.n_mtiles) : *p.n_mtiles;
+    const int total_tiles = max(m_end - p.m_begin, 0) * p.n_tiles;
 
     if (warp == 0) {
         // ================= TMA producer =================
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const dcmoe_mtile mt = p.mtiles[tile / p.n_tiles];
+            const dcmoe_mtile mt = p.mtiles[p.m_begin + tile / p.n_tiles];
             const int nt = tile % p.n_tiles;
             const CUtensorMap* amap = SWIGLU ? (mt.group == p.n_real ? &tmap_a0 : &tmap_a1) : &tmap_a0;
             const int a_row = SWIGLU ? mt.a_row : mt.out_row;
@@ -269,12 +178,12 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
     } else if (warp >= 4) {
         // ================= epilogue =================
         const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
-        const uint32_t slab0 = epi_base + (uint32_t)(wq * 2 * EPI_SLAB);
+        const uint32_t slab0 = epi_base + (uint32_t)(wq * EPI_BUFS * EPI_SLAB);
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t chunk_ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const dcmoe_mtile mt = p.mtiles[tile / p.n_tiles];
+            const dcmoe_mtile mt = p.mtiles[p.m_begin + tile / p.n_tiles];
             const int nt = tile % p.n_tiles;
             const int n_acc = nt == p.n_tiles - 1 ? p.n_last : BN;
             const int n_chunks = SWIGLU ? n_acc / 128 : n_acc / 64;
@@ -289,8 +198,8 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
             for (int j = 0; j < n_chunks; ++j) {
-                const uint32_t slab = slab0 + (chunk_ctr & 1u) * EPI_SLAB;
-                if (lane == 0) tma_wait_read<1>();  // the store that used this slab two chunks ago has drained
+                const uint32_t slab = slab0 + (chunk_ctr % EPI_BUFS) * EPI_SLAB;
+                if (lane == 0) tma_wait_read<EPI_BUFS - 1>();  // the store that last used this slab has drained
                 __syncwarp();
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -354,43 +263,6 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-    if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || sym == nullptr) {
-        set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(err));
-        return nullptr;
-    }
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-    return fn;
-}
-
-// 2-D bf16 row-major tensor [rows, cols], box [box_rows, 64 cols], 128B swizzle
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return DCMOE_ERR_CUDA;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d base=%p", (int)r, (long long)rows,
-                  (long long)cols, box_rows, base);
-        return DCMOE_ERR_CUDA;
-    }
-    return DCMOE_OK;
-}
-
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -405,7 +277,7 @@ int num_sms() {
 
 int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                        int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv,
-                       void* h, void* y, int phase, cudaStream_t stream) {
+                       void* h, void* y, int phase, int group_sel, int max_ctas, cudaStream_t stream) {
     if (T == 0) return DCMOE_OK;
     if (cfg->dtype != DCMOE_BF16) {
         set_error("tcgen05 FFN is bf16 only (fp32 layers use the CUDA-core path, impl = 1)");
@@ -426,13 +298,13 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     CUtensorMap m_x, m_xp, m_w13, m_h_st, m_h_ld, m_w2, m_y_st;
     int rc;
     const int64_t packed_rows = row_capacity - sz.t_pad;
-    if ((rc = make_map(&m_x, x, T, H, BM))) return rc;
-    if ((rc = make_map(&m_xp, x_packed, packed_rows > 0 ? packed_rows : 1, H, BM))) return rc;
-    if ((rc = make_map(&m_w13, w13, (int64_t)G * 2 * Id, H, BN))) return rc;
-    if ((rc = make_map(&m_h_st, h, row_capacity, Id, 32))) return rc;
-    if ((rc = make_map(&m_h_ld, h, row_capacity, Id, BM))) return rc;
-    if ((rc = make_map(&m_w2, w2, (int64_t)G * H, Id, BN))) return rc;
-    if ((rc = make_map(&m_y_st, y, row_capacity, H, 32))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_x, x, T, H, BM))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_xp, x_packed, packed_rows > 0 ? packed_rows : 1, H, BM))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_w13, w13, (int64_t)G * 2 * Id, H, BN))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_h_st, h, row_capacity, Id, 32))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_h_ld, h, row_capacity, Id, BM))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_w2, w2, (int64_t)G * H, Id, BN))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_y_st, y, row_capacity, H, 32))) return rc;
 
     GemmParams p1, p2;
     p1.n_tiles = (int)ceil_div(2 * Id, BN);
@@ -444,13 +316,21 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     p1.mtiles = pv.mtiles;
     p1.n_mtiles = pv.n_mtiles;
     p1.row_scale = row_scale;
+    // group_sel: 0 = every m-tile, 1 = shared-expert tiles only, 2 = routed tiles only (shared tiles come first)
+    const int n_shared_tiles = (int)(sz.t_pad / BM);
+    p1.m_begin = group_sel == 2 ? n_shared_tiles : 0;
+    p1.m_end = group_sel == 1 ? n_shared_tiles : -1;
     p2 = p1;
     p2.n_tiles = (int)ceil_div(H, BN);
     p2.n_last = H - (p2.n_tiles - 1) * BN;
     p2.num_kb = Id / BK;
     p2.w_rows = H;
 
-    dim3 grid((unsigned)num_sms()), block(NUM_THREADS);
+    // DCMOE_FFN_MAX_CTAS (debug / tuning): run the persistent GEMMs on fewer SMs than the chip has, e.g. to leave
+    // SMs to the expert-parallel dispatch / combine kernels that run concurrently
+    int n_ctas = num_sms();
+    if (max_ctas > 0 && max_ctas < n_ctas) n_ctas = max_ctas;
+    dim3 grid((unsigned)n_ctas), block(NUM_THREADS);
     if (phase != 2) {
         ffn_gemm_kernel<true><<<grid, block, SMEM_BYTES, stream>>>(m_x, m_xp, m_w13, m_h_st, p1);
         if ((rc = check_cuda(cudaGetLastError(), "ffn_gemm_kernel<SwiGLU> launch"))) return rc;

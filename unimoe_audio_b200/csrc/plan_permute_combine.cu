@@ -10,7 +10,7 @@
 //                   128-bit loads and written to the r_t packed rows it was routed to.  The slot of
 //                   (token, expert) = segment base + block prefix + rank inside the 16-token block,
 //                   i.e. the stable (ascending token id) permutation.
-//   combine_kernel  replaces core.py:486-488 + utils.py:488-523 (decompress_matrix, scatter into
+//   combine (ep.cu: ep_combine_kernel, one rank)  replaces core.py:486-488 + utils.py:488-523 (decompress_matrix, scatter into
 //                   [T, 8, H] zeros, weighted einsum) and core.py:338-353 (shared-expert adds):
 //                   per token, gather of the shared row + <= n_real routed rows (already weighted by
 //                   the GEMM-1 epilogue), fp32 accumulation in fixed expert order, one store.
@@ -224,80 +224,6 @@ __global__ void __launch_bounds__(128) permute_kernel(const char* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool BF16>
-__global__ void __launch_bounds__(256) combine_kernel(const char* __restrict__ y, const int32_t* __restrict__ slot_of,
-                                                      int64_t T, int H, int n_real, char* __restrict__ out) {
-    constexpr int ESIZE = BF16 ? 2 : 4;
-    constexpr int PER = 16 / ESIZE;  // elements per 128-bit vector
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
-    if (t >= T) return;
-    int my_slot = lane < n_real ? slot_of[t * n_real + lane] : -1;
-    const int n_vec = H * ESIZE / 16;
-    const int64_t row_bytes = (int64_t)H * ESIZE;
-    for (int c0 = 0; c0 < n_vec; c0 += 256) {
-        float acc[8][PER];
-        uint4 v[8];
-        const uint4* src = reinterpret_cast<const uint4*>(y + t * row_bytes);  // shared row: row-space row t
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 32 + lane;
-            v[u] = c < n_vec ? ld_nc_v4(src + c) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (BF16) {
-                acc[u][0] = bf16lo(v[u].x); acc[u][1] = bf16hi(v[u].x);
-                acc[u][2 % PER] = bf16lo(v[u].y); acc[u][3 % PER] = bf16hi(v[u].y);
-                acc[u][4 % PER] = bf16lo(v[u].z); acc[u][5 % PER] = bf16hi(v[u].z);
-                acc[u][6 % PER] = bf16lo(v[u].w); acc[u][7 % PER] = bf16hi(v[u].w);
-            } else {
-                acc[u][0] = __uint_as_float(v[u].x); acc[u][1] = __uint_as_float(v[u].y);
-                acc[u][2] = __uint_as_float(v[u].z); acc[u][3] = __uint_as_float(v[u].w);
-            }
-        }
-        for (int e = 0; e < n_real; ++e) {
-            const int slot = __shfl_sync(kFull, my_slot, e);
-            if (slot < 0) continue;  // warp-uniform
-            const uint4* s2 = reinterpret_cast<const uint4*>(y + (int64_t)slot * row_bytes);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c0 + u * 32 + lane;
-                v[u] = c < n_vec ? ld_nc_v4(s2 + c) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (BF16) {
-                    acc[u][0] += bf16lo(v[u].x); acc[u][1] += bf16hi(v[u].x);
-                    acc[u][2 % PER] += bf16lo(v[u].y); acc[u][3 % PER] += bf16hi(v[u].y);
-                    acc[u][4 % PER] += bf16lo(v[u].z); acc[u][5 % PER] += bf16hi(v[u].z);
-                    acc[u][6 % PER] += bf16lo(v[u].w); acc[u][7 % PER] += bf16hi(v[u].w);
-                } else {
-                    acc[u][0] += __uint_as_float(v[u].x); acc[u][1] += __uint_as_float(v[u].y);
-                    acc[u][2] += __uint_as_float(v[u].z); acc[u][3] += __uint_as_float(v[u].w);
-                }
-            }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out + t * row_bytes);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int c = c0 + u * 32 + lane;
-            if (c >= n_vec) continue;
-            uint4 o;
-            if (BF16) {
-                o.x = pack_bf16(acc[u][0], acc[u][1]);
-                o.y = pack_bf16(acc[u][2 % PER], acc[u][3 % PER]);
-                o.z = pack_bf16(acc[u][4 % PER], acc[u][5 % PER]);
-                o.w = pack_bf16(acc[u][6 % PER], acc[u][7 % PER]);
-            } else {
-                o.x = __float_as_uint(acc[u][0]); o.y = __float_as_uint(acc[u][1]);
-                o.z = __float_as_uint(acc[u][2]); o.w = __float_as_uint(acc[u][3]);
-            }
-            st_na_v4(dst + c, o);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Weight packing: W13[group] rows = blocks of 64 gate rows followed by the matching 64 up rows;
 // W2[group] = down_proj, shared experts concatenated along K.
@@ -355,19 +281,6 @@ int launch_permute(const void* x, const int32_t* expert_mask, const void* gw, in
                                                       cfg->n_real, n_dyn, cfg->n_fix, (int)sz.t_pad, pv,
                                                       (char*)x_packed, slot_of, row_token, row_scale);
     return check_cuda(cudaGetLastError(), "permute_kernel launch");
-}
-
-int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out,
-                   cudaStream_t stream) {
-    if (T == 0) return DCMOE_OK;
-    dim3 grid((unsigned)ceil_div(T, 8)), block(256);
-    if (cfg->dtype == DCMOE_BF16)
-        combine_kernel<true><<<grid, block, 0, stream>>>((const char*)y, slot_of, T, cfg->hidden_size, cfg->n_real,
-                                                         (char*)out);
-    else
-        combine_kernel<false><<<grid, block, 0, stream>>>((const char*)y, slot_of, T, cfg->hidden_size, cfg->n_real,
-                                                          (char*)out);
-    return check_cuda(cudaGetLastError(), "combine_kernel launch");
 }
 
 int launch_pack(const void* gate_proj, const void* up_proj, const void* down_proj, int group, int part,

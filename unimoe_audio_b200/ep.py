@@ -124,8 +124,15 @@ class ExpertParallelDCMoE:
         self._peer = None
         self._imported = []
         self._flag = None
-        self.kernels_per_step = 7  # router, plan, ep_plan, ep_dispatch, ffn gemm-1, ffn gemm-2, ep_combine
+        self.kernels_per_step = 11  # router, plan, ep_plan, shared scales, dispatch, 4 x ffn gemm, combine x 2
         self.row_capacity = 0
+        import os
+        self.overlap = os.environ.get("DCMOE_EP_OVERLAP", "1") != "0"   # comm stream under the shared experts' GEMMs
+        self.comm_ctas = int(os.environ.get("DCMOE_EP_COMM_CTAS", "148"))   # grid cap of dispatch / partial combine (0 = full)
+        self.gemm_ctas = int(os.environ.get("DCMOE_EP_GEMM_CTAS", "0"))   # CTAs of the shared GEMMs that run under comm (0 = all SMs)
+        self._side = None
+        self._local_cfg = None
+        self._partial = None
 
     # ------------------------------------------------------------------ setup
     def pack_local_weights(self):
@@ -201,45 +208,55 @@ class ExpertParallelDCMoE:
         hook("plan")
         return vec
 
-    def phase_dispatch(self, all_counts: torch.Tensor):
-        lib = _lib.load()
-        ws, d = self.ws, self.m.dims
-        hook = self.m.stage_hook or (lambda _n: None)
-        cfg = d.c_config(ws.dtype)
-        st = torch.cuda.current_stream().cuda_stream
-        self._all_counts = all_counts.contiguous()
-        _lib.check(lib.dcmoe_ep_plan(self._all_counts.data_ptr(), self.rank, self.world, ws.T, ws.row_capacity, cfg,
-                                     ws.plan.data_ptr(), ws.ep_meta.data_ptr(), st), "dcmoe_ep_plan")
-        hook("ep_plan")
-        _, _, mask, gw = self._route
-        xp, rs, _y = self._peer
-        _lib.check(lib.dcmoe_ep_dispatch(self._x.data_ptr(), mask.data_ptr(), gw.data_ptr(), ws.T, ws.row_capacity, cfg,
-                                         ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
-                                         ws.slot_of.data_ptr(), st), "dcmoe_ep_dispatch")
-        hook("ep_dispatch")
-
-    def phase_ffn(self):
+    def phase_plan(self, all_counts: torch.Tensor):
+        """ep_plan: row-space layout of this rank + destinations of its rows (+ shared-expert row scales)."""
         lib = _lib.load()
         ws = self.ws
         hook = self.m.stage_hook or (lambda _n: None)
-        cfg = self.local_dims.c_config(ws.dtype)
+        st = torch.cuda.current_stream().cuda_stream
+        self._all_counts = all_counts.contiguous()
+        _, _, _mask, gw = self._route
+        _lib.check(lib.dcmoe_ep_plan(self._all_counts.data_ptr(), self.rank, self.world, ws.T, ws.row_capacity, ws.cfg,
+                                     ws.plan.data_ptr(), ws.ep_meta.data_ptr(), gw.data_ptr(), ws.row_scale.data_ptr(), st),
+                   "dcmoe_ep_plan")
+        hook("ep_plan")
+
+    def phase_dispatch(self):
+        lib = _lib.load()
+        ws = self.ws
+        st = torch.cuda.current_stream().cuda_stream
+        _, _, mask, gw = self._route
+        xp, rs, _y = self._peer
+        _lib.check(lib.dcmoe_ep_dispatch(self._x.data_ptr(), mask.data_ptr(), gw.data_ptr(), ws.T, ws.row_capacity, ws.cfg,
+                                         ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
+                                         ws.slot_of.data_ptr(), self.comm_ctas, st), "dcmoe_ep_dispatch")
+
+    def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0):
+        """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2 = all / shared-expert / routed row tiles."""
+        lib = _lib.load()
+        ws = self.ws
+        if self._local_cfg is None:
+            self._local_cfg = self.local_dims.c_config(ws.dtype)
         impl = self.m.ffn_impl if self.m.ffn_impl is not None else (0 if ws.dtype == torch.bfloat16 else 1)
         st = torch.cuda.current_stream().cuda_stream
-        for phase, name in ((1, "ffn_gemm1"), (2, "ffn_gemm2")):
-            _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
-                                             self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, cfg,
-                                             ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl, phase, st),
-                       "dcmoe_grouped_ffn")
-            hook(name)
+        _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
+                                         self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, self._local_cfg,
+                                         ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl,
+                                         phase | (group_sel << 4) | (max_ctas << 8), st),
+                   "dcmoe_grouped_ffn")
+        if name and self.m.stage_hook:
+            self.m.stage_hook(name)
 
-    def phase_combine(self, out: torch.Tensor):
+    def phase_combine(self, out: Optional[torch.Tensor], mode: int = 0):
         lib = _lib.load()
-        ws, d = self.ws, self.m.dims
-        hook = self.m.stage_hook or (lambda _n: None)
+        ws = self.ws
         _xp, _rs, y = self._peer
-        _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr(), y, ws.slot_of.data_ptr(), ws.T, d.c_config(ws.dtype), self.world,
-                                        out.data_ptr(), torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
-        hook("ep_combine")
+        if mode != 0 and self._partial is None:
+            self._partial = torch.empty((max(ws.T, 1), self.m.dims.hidden_size), dtype=torch.float32, device=ws.device)
+        _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr(), y, ws.slot_of.data_ptr(), ws.T, ws.cfg, self.world, mode,
+                                        None if self._partial is None else self._partial.data_ptr(),
+                                        None if out is None else out.data_ptr(), self.comm_ctas if mode == 1 else 0,
+                                        torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
 
     # ------------------------------------------------------------------ distributed forward
     @torch.no_grad()
@@ -258,18 +275,55 @@ class ExpertParallelDCMoE:
         if self._peer is None:
             self._exchange_handles()
         hook = self.m.stage_hook or (lambda _n: None)
+        main = torch.cuda.current_stream()
         vec = self.phase_route(x, attention_mask, router_logits)
         all_counts = torch.empty((self.world, vec.numel()), dtype=torch.int32, device=x.device)
         dist.all_gather_into_tensor(all_counts, vec, group=self.group)          # also the "buffers are free" barrier
         hook("allgather_counts")
-        self.phase_dispatch(all_counts)
-        dist.all_reduce(self._flag, group=self.group)                            # every rank's rows have landed
-        hook("barrier_dispatch")
-        self.phase_ffn()
-        dist.all_reduce(self._flag, group=self.group)                            # every owner's y is complete
-        hook("barrier_ffn")
+        self.phase_plan(all_counts)
         out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
-        self.phase_combine(out.view(T, H))
+        tcgen05 = (self.m.ffn_impl in (None, 0)) and x.dtype == torch.bfloat16
+        if not (self.overlap and tcgen05):
+            self.phase_dispatch()
+            hook("ep_dispatch")
+            dist.all_reduce(self._flag, group=self.group)                        # every rank's rows have landed
+            hook("barrier_dispatch")
+            self.phase_ffn(1, 0, "ffn_gemm1")
+            self.phase_ffn(2, 0, "ffn_gemm2")
+            dist.all_reduce(self._flag, group=self.group)                        # every owner's y is complete
+            hook("barrier_ffn")
+            self.phase_combine(out.view(T, H), 0)
+            hook("ep_combine")
+        else:
+            # comm stream: dispatch over NVLink + barrier, while the main stream runs the shared experts' GEMM-1
+            if self._side is None:
+                self._side = torch.cuda.Stream(x.device)
+                self._ev = [torch.cuda.Event() for _ in range(4)]
+                self._flag2 = torch.zeros(1, dtype=torch.int32, device=x.device)
+            side, ev = self._side, self._ev
+            ev[0].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev[0])
+                self.phase_dispatch()
+                dist.all_reduce(self._flag2, group=self.group)                   # barrier 1 (on the comm stream)
+                ev[1].record(side)
+            self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas)             # overlaps the dispatch
+            main.wait_event(ev[1])
+            hook("wait_dispatch")
+            self.phase_ffn(1, 2, "ffn_gemm1_routed")
+            self.phase_ffn(2, 2, "ffn_gemm2_routed")
+            dist.all_reduce(self._flag, group=self.group)                        # barrier 2: routed y complete everywhere
+            hook("barrier_ffn")
+            ev[2].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev[2])
+                self.phase_combine(None, 1)                                      # routed rows over NVLink -> fp32 partial
+                ev[3].record(side)
+            self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)             # overlaps the combine gather
+            main.wait_event(ev[3])
+            hook("wait_combine")
+            self.phase_combine(out.view(T, H), 2)
+            hook("ep_combine_final")
         logits, top_k, mask, gw = self._route
         return out, logits, top_k, mask, gw, self._aux
 
@@ -278,8 +332,9 @@ class LocalRanks:
     """R virtual ranks in one process on one GPU: the same kernels and call order as the distributed forward,
     with the collectives replaced by torch ops on the ranks' tensors.  Test / debugging aid."""
 
-    def __init__(self, module: DCMoE, world: int):
+    def __init__(self, module: DCMoE, world: int, split: bool = False):
         self.world = world
+        self.split = split
         self.ranks = [ExpertParallelDCMoE(module, group=None, rank=r, world=world) for r in range(world)]
 
     @torch.no_grad()
@@ -297,14 +352,35 @@ class LocalRanks:
         vecs = [ep.phase_route(flat[r], None if attention_masks is None else attention_masks[r]) for r, ep in enumerate(self.ranks)]
         all_counts = torch.stack(vecs).contiguous()
         for ep in self.ranks:
-            ep.phase_dispatch(all_counts)
-        for ep in self.ranks:
-            ep.phase_ffn()
-        outs = []
-        for r, ep in enumerate(self.ranks):
-            out = torch.empty_like(flat[r])
-            ep.phase_combine(out)
-            logits, top_k, mask, gw = ep._route
-            outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
+            ep.phase_plan(all_counts)
+        if not self.split:
+            for ep in self.ranks:
+                ep.phase_dispatch()
+            for ep in self.ranks:
+                ep.phase_ffn(0, 0)
+            outs = []
+            for r, ep in enumerate(self.ranks):
+                out = torch.empty_like(flat[r])
+                ep.phase_combine(out, 0)
+                logits, top_k, mask, gw = ep._route
+                outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
+        else:   # the kernel sequence of the overlapped schedule (run serially here)
+            for ep in self.ranks:
+                ep.phase_ffn(1, 1)          # shared GEMM-1 needs nothing from the dispatch
+            for ep in self.ranks:
+                ep.phase_dispatch()
+            for ep in self.ranks:
+                ep.phase_ffn(1, 2)
+                ep.phase_ffn(2, 2)
+            for ep in self.ranks:
+                ep.phase_combine(None, 1)
+            for ep in self.ranks:
+                ep.phase_ffn(2, 1)
+            outs = []
+            for r, ep in enumerate(self.ranks):
+                out = torch.empty_like(flat[r])
+                ep.phase_combine(out, 2)
+                logits, top_k, mask, gw = ep._route
+                outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
         self.all_counts = all_counts
         return outs
