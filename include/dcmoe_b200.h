@@ -86,6 +86,10 @@ typedef struct dcmoe_plan_layout {
     int64_t n_mtiles;       /* [1] int32                 number of valid entries in mtiles         */
     int64_t aux_loss;       /* [1] float                 audio_load_balancing_loss_func result     */
     int64_t mtiles;         /* [max_mtiles] dcmoe_mtile                                          */
+    int64_t n_pairs;        /* [1] int32                 number of valid entries in pairs          */
+    int64_t pairs;          /* [max_mtiles] int32        tile pairs for the 2-CTA GEMM: index of the first */
+                            /*                           m-tile | (1 << 30 if the next tile of the same   */
+                            /*                           group completes the 256-row pair)              */
     int64_t total;          /* == plan_bytes */
 } dcmoe_plan_layout;
 
@@ -152,8 +156,9 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *   w2           [n_real+1, H, I_d] D
  *   h            [row_capacity, I_d] D    silu(gate) * up * row_scale   (scratch)
  *   y            [row_capacity, H] D      already weighted expert outputs
- *   impl         0 = tcgen05/TMEM/TMA grouped GEMM (bf16 only), 1 = CUDA-core fp32-accumulate GEMM
- *                (the fp32 layer path; also usable with bf16 for cross-checking)
+ *   impl         0 = tcgen05/TMEM/TMA grouped GEMM, one CTA per tile (bf16 only); 2 = the same on CTA pairs
+ *                (tcgen05.mma.cta_group::2, 256-row tiles); 1 = CUDA-core fp32-accumulate GEMM (the fp32 layer
+ *                path; also usable with bf16 for cross-checking)
  *   phase        low 4 bits: 0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
  *                put CUDA events between the two launches.  Bits 4-5 select the tile group (tcgen05 only):
  *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism

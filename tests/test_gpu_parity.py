@@ -327,3 +327,23 @@ def test_cuda_graph_replay_matches_eager(B, S, dev):
     o = O.forward(x.cpu(), W, None, logits=ref[1].cpu())
     assert torch.equal(ref[3].cpu(), o.expert_mask)
     _check_layer(ref[0].reshape(B * S, 2048), o.final_hidden_states.reshape(B * S, 2048), dt)
+
+
+@pytest.mark.parametrize("B,S", [(4, 640), (1, 1), (3, 171), (1, 129)])
+def test_cta_pair_ffn_matches_single_cta_ffn(B, S, dev):
+    """tcgen05.mma.cta_group::2 (256-row tile pairs) against the one-CTA-per-tile kernel: same rows, same K order."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=2)
+    x = torch.randn(B, S, 2048, generator=torch.Generator().manual_seed(31 + S)).to(dt).to(dev)
+    m.ffn_impl = 0
+    out1 = [t.clone() for t in m(x, None, None)]
+    m.ffn_impl = 2
+    out2 = m(x, None, None)
+    torch.cuda.synchronize()
+    m.ffn_impl = None
+    a, b = out2[0].float(), out1[0].float()
+    assert torch.equal(out2[3], out1[3])
+    assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
+    assert ((a - b).norm() / b.norm()).item() < 2e-3
+    ref = O.forward(x.cpu(), W, None, logits=out2[1].cpu())
+    _check_layer(out2[0].reshape(B * S, 2048), ref.final_hidden_states.reshape(B * S, 2048), dt)

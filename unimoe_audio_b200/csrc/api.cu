@@ -124,6 +124,8 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     l->n_mtiles = off;     off = align_up(off + 4, 16);
     l->aux_loss = off;     off = align_up(off + 4, 16);
     l->mtiles = off;       off = align_up(off + sz->max_mtiles * (int64_t)sizeof(dcmoe_mtile), 16);
+    l->n_pairs = off;      off = align_up(off + 4, 16);
+    l->pairs = off;        off = align_up(off + sz->max_mtiles * 4, 16);
     l->total = off;
     sz->plan_bytes = off;
     return DCMOE_OK;
@@ -142,6 +144,8 @@ int launch_ffn_simt(const void*, const void*, const void*, const void*, const fl
                     const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                        const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
+                            const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 
 static int require_device() {
     int n = 0;
@@ -252,6 +256,11 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     if (phase < 0 || phase > 2) { set_error("dcmoe_grouped_ffn: phase must be 0, 1 or 2"); return DCMOE_ERR_INVALID; }
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
+    if (impl == 2) {
+        if (cfg->dtype != DCMOE_BF16) { set_error("tcgen05 FFN is bf16 only"); return DCMOE_ERR_INVALID; }
+        return launch_ffn_tcgen05_2cta(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase, group_sel,
+                                       max_ctas, (cudaStream_t)stream);
+    }
     if (impl == 0) return launch_ffn_tcgen05(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
                                              phase, group_sel, max_ctas, (cudaStream_t)stream);
     if (impl == 1) {

@@ -34,6 +34,8 @@ struct PlanView {
     int32_t* n_mtiles;
     float* aux_loss;
     dcmoe_mtile* mtiles;
+    int32_t* n_pairs;
+    int32_t* pairs;
 };
 
 inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
@@ -47,6 +49,8 @@ inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
     v.n_mtiles = reinterpret_cast<int32_t*>(p + l.n_mtiles);
     v.aux_loss = reinterpret_cast<float*>(p + l.aux_loss);
     v.mtiles = reinterpret_cast<dcmoe_mtile*>(p + l.mtiles);
+    v.n_pairs = reinterpret_cast<int32_t*>(p + l.n_pairs);
+    v.pairs = reinterpret_cast<int32_t*>(p + l.pairs);
     return v;
 }
 

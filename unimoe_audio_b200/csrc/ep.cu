@@ -108,6 +108,35 @@ __global__ void __launch_bounds__(256) ep_plan_kernel(const int32_t* __restrict_
         }
         pv.mtiles[i] = mt;
     }
+    // tile pairs for the 2-CTA GEMM: consecutive m-tiles of one group, two at a time
+    {
+        __shared__ int s_pair0[kMaxDyn + 2];
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            s_pair0[0] = 0;                                   // group order: shared tiles, then segments 0..n_loc-1
+            acc += (n_shared_tiles + 1) / 2;
+            for (int e = 0; e < n_loc; ++e) {
+                s_pair0[e + 1] = acc;
+                acc += (s_tile0[e + 1] - s_tile0[e] + 1) / 2;
+            }
+            s_pair0[n_loc + 1] = acc;
+            *pv.n_pairs = acc < max_mtiles ? acc : max_mtiles;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < total && i < max_mtiles; i += blockDim.x) {
+            int start, pbase, end;
+            if (i < n_shared_tiles) { start = 0; pbase = s_pair0[0]; end = n_shared_tiles; }
+            else {
+                int e = 0;
+                while (e + 1 < n_loc && i >= s_tile0[e + 1]) ++e;
+                start = s_tile0[e]; pbase = s_pair0[e + 1]; end = s_tile0[e + 1];
+            }
+            if (((i - start) & 1) == 0) {
+                const int pi = pbase + ((i - start) >> 1);
+                if (pi < max_mtiles) pv.pairs[pi] = i | ((i + 1 < end) ? (1 << 30) : 0);
+            }
+        }
+    }
 }
 
 // shared-expert row scales (gw[t, n_dyn], gw[t, n_dyn + 1]) of the local rows [0, T): written here, before the

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace dcmoe {
 
@@ -548,6 +549,193 @@ router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-fed persistent router (bf16, the production path).
+// One CTA per SM, 21 warps:
+//   warp 0       TMA producer: the 16-token x block (16 x H bf16 = 64 KB) is fetched as 64-column boxes
+//                (cp.async.bulk.tensor.2d, 128B swizzle) into a 2-stage smem ring -- up to 128 KB in flight per SM
+//                with no register cost, which is what it takes to stream HBM at full rate from ~7 blocks per SM;
+//   warps 1-4    gate MMA: ldmatrix.x4 (swizzled) + mma.sync.m16n8k16 against W_g held in smem in fragment order,
+//                K split four ways, partial logits into a 4-stage smem ring;
+//   warps 5-20   routing: two groups of 8 warps (one 16-token block per group per round, half-warp per token)
+//                running the shuffle/exp chains of route_token<> while the next blocks stream in.
+// mbarriers pace the x ring; named barriers (bar.arrive / bar.sync) pace the logits ring.
+constexpr int kTmaThreads = 21 * 32;
+constexpr int kXStageBytes = kRouterBlock * 2048 * 2;   // sized for H = 2048 (checked at launch: H <= 2048)
+constexpr int kXStages = 2;
+constexpr int kWfBytes = (2048 / 16) * 2 * 32 * 8;      // W_g fragments: [k16][n-tile][lane] x 8 B
+constexpr int kRedStages = 4;
+constexpr int kRouterSmem = kXStages * kXStageBytes + kWfBytes + kRedStages * 4 * kRouterBlock * 16 * 4 +
+                            2 * 2 * kRouterBlock * kMaxDyn * 4 + 64 + 1024;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+
+template <int NDYN, int NE>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wg,
+                  const int32_t* __restrict__ attn_mask, int64_t T, int H, int n_blocks, RouteConsts rc,
+                  __nv_bfloat16* __restrict__ logits_out, int64_t* __restrict__ top_k,
+                  int32_t* __restrict__ expert_mask, __nv_bfloat16* __restrict__ gw_out,
+                  int32_t* __restrict__ block_counts, float* __restrict__ block_probs) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t xs = base;                                                 // [kXStages][H/64][16 rows][128 B]
+    uint2* wf = reinterpret_cast<uint2*>(gbase + kXStages * kXStageBytes);    // [H/16][2][32]
+    float* red = reinterpret_cast<float*>(gbase + kXStages * kXStageBytes + kWfBytes);   // [4][4][16][16]
+    int* s_cnt = reinterpret_cast<int*>(red + kRedStages * 4 * kRouterBlock * 16);       // [2 groups][16][16]
+    float* s_prob = reinterpret_cast<float*>(s_cnt + 2 * kRouterBlock * kMaxDyn);
+    const uint32_t bars = smem_u32(s_prob + 2 * kRouterBlock * kMaxDyn);
+    auto x_full = [&](int s) { return bars + 8u * s; };
+    auto x_empty = [&](int s) { return bars + 8u * (kXStages + s); };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int E = NE ? NE : rc.E;
+    const int n_dyn = NDYN ? NDYN : rc.n_dyn;
+    const int n_chunks = H >> 6;   // 64-column boxes per row block
+    if (tid == 0) {
+        prefetch_tmap(&tmap_x);
+        for (int s = 0; s < kXStages; ++s) {
+            mbar_init(x_full(s), 1);
+            mbar_init(x_empty(s), 4);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();   // barriers initialised; the producer starts streaming x right away
+    if (warp != 0) {
+        // W_g -> smem in mma B-fragment order (done by the 20 non-producer warps while the first x blocks are in
+        // flight): wf[k16][nt][lane] = {W[n][16 k16 + 2 tq .. +1], W[n][16 k16 + 8 + 2 tq .. +1]}, n = 8 nt + lane / 4,
+        // tq = lane % 4; rows n >= E are zero.  One 16-byte load (8 consecutive k of one row) feeds four entries.
+        uint32_t* wf32 = reinterpret_cast<uint32_t*>(wf);
+        const int n_kc = H >> 3;                       // 16-byte chunks per row
+        for (int i = tid - 32; i < 16 * n_kc; i += kTmaThreads - 32) {
+            const int n = i / n_kc, kc = i - n * n_kc;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (n < E) v = ld_ca_v4(wg + (int64_t)n * H + kc * 8);
+            const int k16 = kc >> 1, hi = kc & 1, nt = n >> 3, g = n & 7;
+            uint32_t* dst = wf32 + (((k16 * 2 + nt) * 32 + g * 4) << 1) + hi;
+            dst[0] = v.x;
+            dst[2] = v.y;
+            dst[4] = v.z;
+            dst[6] = v.w;
+        }
+        named_bar_sync(13, kTmaThreads - 32);
+    }
+
+    constexpr int kFullCount = 128 + 256;   // gate warps + one routing group
+    if (warp == 0) {
+        // ================= TMA producer =================
+        int it = 0;
+        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const int st = it & (kXStages - 1);
+            const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
+            mbar_wait(x_empty(st), ph ^ 1u);
+            if (lane == 0) {
+                mbar_expect_tx(x_full(st), (uint32_t)(kRouterBlock * H * 2));
+                for (int c = 0; c < n_chunks; ++c)
+                    tma_load_2d(xs + st * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
+                                x_full(st));
+            }
+            __syncwarp();
+        }
+    } else if (warp <= 4) {
+        // ================= gate MMA warps =================
+        const int wq = warp - 1;
+        const int chunks_per_warp = n_chunks >> 2;
+        const int g = lane >> 2, tq = lane & 3;
+        const int mi = lane >> 3;                              // ldmatrix: lane -> (matrix, row)
+        const int lrow = (lane & 7) + (mi & 1) * 8;
+        int it = 0;
+        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const int st = it & (kXStages - 1);
+            const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
+            const int rs = it & (kRedStages - 1);
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mbar_wait(x_full(st), ph);
+            for (int cc = 0; cc < chunks_per_warp; ++cc) {
+                const int c = wq * chunks_per_warp + cc;
+                const uint32_t tile = xs + st * kXStageBytes + c * (kRouterBlock * 128);
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int lchunk = 2 * s4 + (mi >> 1);
+                    uint32_t a0, a1, a2, a3;
+                    ldmatrix_x4(tile + lrow * 128 + ((lchunk ^ (lrow & 7)) << 4), a0, a1, a2, a3);
+                    const int k16 = c * 4 + s4;
+                    const uint2 b0 = wf[(k16 * 2 + 0) * 32 + lane];
+                    const uint2 b1 = wf[(k16 * 2 + 1) * 32 + lane];
+                    mma_bf16_16816(c0, a0, a1, a2, a3, b0.x, b0.y);
+                    mma_bf16_16816(c1, a0, a1, a2, a3, b1.x, b1.y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_empty(st));           // this warp is done reading the x stage
+            if (it >= kRedStages) named_bar_sync(5 + rs, kFullCount);
+            float* r = red + ((rs * 4 + wq) * kRouterBlock) * 16;
+            r[g * 16 + 2 * tq] = c0[0];
+            r[g * 16 + 2 * tq + 1] = c0[1];
+            r[(g + 8) * 16 + 2 * tq] = c0[2];
+            r[(g + 8) * 16 + 2 * tq + 1] = c0[3];
+            r[g * 16 + 8 + 2 * tq] = c1[0];
+            r[g * 16 + 8 + 2 * tq + 1] = c1[1];
+            r[(g + 8) * 16 + 8 + 2 * tq] = c1[2];
+            r[(g + 8) * 16 + 8 + 2 * tq + 1] = c1[3];
+            named_bar_arrive(1 + rs, kFullCount);
+        }
+    } else {
+        // ================= routing warps: group 0 = warps 5-12, group 1 = warps 13-20 =================
+        const int grp = (warp - 5) >> 3, rw_ = (warp - 5) & 7;
+        const int half = lane >> 4, j = lane & 15;
+        const int gtid = tid - (5 + grp * 8) * 32;
+        int* cnt = s_cnt + grp * kRouterBlock * kMaxDyn;
+        float* prob = s_prob + grp * kRouterBlock * kMaxDyn;
+        int it = grp;
+        for (int blk = blockIdx.x + grp * gridDim.x; blk < n_blocks; blk += 2 * gridDim.x, it += 2) {
+            const int rs = it & (kRedStages - 1);
+            const int64_t tok0 = (int64_t)blk * kRouterBlock;
+            const int tl = rw_ * 2 + half;
+            const int64_t t = tok0 + tl;
+            const bool valid = t < T;
+            named_bar_sync(1 + rs, kFullCount);
+            float l = 0.0f;
+            if (j < E) {
+                const float* r = red + (rs * 4 * kRouterBlock + tl) * 16 + j;
+                l = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[kRouterBlock * 16]), r[2 * kRouterBlock * 16]), r[3 * kRouterBlock * 16]);
+                l = bf16_round(l);
+            }
+            if ((int64_t)blk + (int64_t)kRedStages * gridDim.x < n_blocks) named_bar_arrive(5 + rs, kFullCount);
+            const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
+            int raw, mk;
+            float gw, ga;
+            route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            if (valid && j < E) {
+                logits_out[t * E + j] = __float2bfloat16_rn(l);
+                gw_out[t * E + j] = __float2bfloat16_rn(gw);
+                expert_mask[t * E + j] = mk;
+                if (j == 0) top_k[t] = raw;
+            }
+            cnt[tl * kMaxDyn + j] = (valid && j < n_dyn) ? mk : 0;
+            prob[tl * kMaxDyn + j] = (valid && j < n_dyn) ? ga : 0.0f;
+            named_bar_sync(9 + grp, 256);
+            if (gtid < n_dyn) {
+                int c = 0;
+                float pr = 0.0f;
+#pragma unroll
+                for (int r = 0; r < kRouterBlock; ++r) {
+                    c += cnt[r * kMaxDyn + gtid];
+                    pr = __fadd_rn(pr, prob[r * kMaxDyn + gtid]);
+                }
+                block_counts[(int64_t)blk * n_dyn + gtid] = c;
+                block_probs[(int64_t)blk * n_dyn + gtid] = pr;
+            }
+            named_bar_sync(11 + grp, 256);   // stats buffer may be rewritten
+        }
+    }
+}
+
 }  // namespace
 
 int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
@@ -577,13 +765,36 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
     static int ws_mode = -1;
     if (ws_mode < 0) {
-        const char* env = getenv("DCMOE_ROUTER_WS");      // debug switch: 0 = one CTA per block kernel
-        ws_mode = (env && env[0] == '0') ? 0 : 1;
+        const char* env = getenv("DCMOE_ROUTER_MODE");   // debug switch: 0 = one CTA per block, 1 = warp-specialised
+        ws_mode = env ? atoi(env) : 2;                   // (register-staged loads), 2 = TMA-fed persistent (default)
     }
-    if (bf16 && logits_in == nullptr && ws_mode == 1) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouterSmem), "cudaFuncSetAttribute(router_tma<9,11>)");
+            if (rc2) return rc2;
+            rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouterSmem), "cudaFuncSetAttribute(router_tma<0,0>)");
+            if (rc2) return rc2;
+            attr_done = true;
+        }
+        CUtensorMap tmap;
+        int rc2 = make_tensor_map_bf16(&tmap, x, T, cfg->hidden_size, kRouterBlock);
+        if (rc2) return rc2;
+        dim3 g2((unsigned)(n_blocks < sms ? n_blocks : sms)), b2(kTmaThreads);
+        if (ref_shape)
+            router_tma_kernel<9, 11><<<g2, b2, kRouterSmem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
+                (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        else
+            router_tma_kernel<0, 0><<<g2, b2, kRouterSmem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
+                (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        return check_cuda(cudaGetLastError(), "router_tma_kernel launch");
+    }
+    if (bf16 && logits_in == nullptr && ws_mode >= 1) {
         const int64_t want = 2 * (int64_t)sms;
         dim3 g2((unsigned)(n_blocks < want ? n_blocks : want)), b2(kWsThreads);
         if (ref_shape)

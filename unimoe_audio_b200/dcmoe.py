@@ -81,6 +81,9 @@ class _MoE(nn.Module):              # UniMoEAudioMoE, core.py:496-523
                                        self.num_local_experts)
 
 
+# bf16 FFN implementation: 0 = tcgen05 one CTA per 128-row tile, 2 = tcgen05 CTA pairs (cta_group::2, 256-row tiles)
+_DEFAULT_BF16_IMPL = int(__import__("os").environ.get("DCMOE_FFN_IMPL", "0"))
+
 _WORKSPACES: Dict[tuple, Workspace] = {}
 
 
@@ -242,7 +245,7 @@ class DCMoE(nn.Module):
         if T > 0:
             ops.permute(x, mask, gw, ws)
             hook("permute")
-            impl = self.ffn_impl if self.ffn_impl is not None else (0 if dt == torch.bfloat16 else 1)
+            impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
             ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
             hook("ffn_gemm1")
             ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)

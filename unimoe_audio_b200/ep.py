@@ -221,7 +221,7 @@ class ExpertParallelDCMoE:
                    "dcmoe_ep_plan")
         hook("ep_plan")
 
-    def phase_dispatch(self):
+    def phase_dispatch(self, max_ctas: int = 0):
         lib = _lib.load()
         ws = self.ws
         st = torch.cuda.current_stream().cuda_stream
@@ -229,7 +229,7 @@ class ExpertParallelDCMoE:
         xp, rs, _y = self._peer
         _lib.check(lib.dcmoe_ep_dispatch(self._x.data_ptr(), mask.data_ptr(), gw.data_ptr(), ws.T, ws.row_capacity, ws.cfg,
                                          ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
-                                         ws.slot_of.data_ptr(), self.comm_ctas, st), "dcmoe_ep_dispatch")
+                                         ws.slot_of.data_ptr(), max_ctas, st), "dcmoe_ep_dispatch")
 
     def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0):
         """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2 = all / shared-expert / routed row tiles."""
@@ -237,7 +237,8 @@ class ExpertParallelDCMoE:
         ws = self.ws
         if self._local_cfg is None:
             self._local_cfg = self.local_dims.c_config(ws.dtype)
-        impl = self.m.ffn_impl if self.m.ffn_impl is not None else (0 if ws.dtype == torch.bfloat16 else 1)
+        from .dcmoe import _DEFAULT_BF16_IMPL
+        impl = self.m.ffn_impl if self.m.ffn_impl is not None else (_DEFAULT_BF16_IMPL if ws.dtype == torch.bfloat16 else 1)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
                                          self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, self._local_cfg,
@@ -247,7 +248,7 @@ class ExpertParallelDCMoE:
         if name and self.m.stage_hook:
             self.m.stage_hook(name)
 
-    def phase_combine(self, out: Optional[torch.Tensor], mode: int = 0):
+    def phase_combine(self, out: Optional[torch.Tensor], mode: int = 0, max_ctas: int = 0):
         lib = _lib.load()
         ws = self.ws
         _xp, _rs, y = self._peer
@@ -255,7 +256,7 @@ class ExpertParallelDCMoE:
             self._partial = torch.empty((max(ws.T, 1), self.m.dims.hidden_size), dtype=torch.float32, device=ws.device)
         _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr(), y, ws.slot_of.data_ptr(), ws.T, ws.cfg, self.world, mode,
                                         None if self._partial is None else self._partial.data_ptr(),
-                                        None if out is None else out.data_ptr(), self.comm_ctas if mode == 1 else 0,
+                                        None if out is None else out.data_ptr(), max_ctas,
                                         torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
 
     # ------------------------------------------------------------------ distributed forward
@@ -282,7 +283,7 @@ class ExpertParallelDCMoE:
         hook("allgather_counts")
         self.phase_plan(all_counts)
         out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
-        tcgen05 = (self.m.ffn_impl in (None, 0)) and x.dtype == torch.bfloat16
+        tcgen05 = (self.m.ffn_impl in (None, 0, 2)) and x.dtype == torch.bfloat16
         if not (self.overlap and tcgen05):
             self.phase_dispatch()
             hook("ep_dispatch")
@@ -304,7 +305,7 @@ class ExpertParallelDCMoE:
             ev[0].record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev[0])
-                self.phase_dispatch()
+                self.phase_dispatch(self.comm_ctas)
                 dist.all_reduce(self._flag2, group=self.group)                   # barrier 1 (on the comm stream)
                 ev[1].record(side)
             self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas)             # overlaps the dispatch
@@ -317,7 +318,7 @@ class ExpertParallelDCMoE:
             ev[2].record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev[2])
-                self.phase_combine(None, 1)                                      # routed rows over NVLink -> fp32 partial
+                self.phase_combine(None, 1, self.comm_ctas)                      # routed rows over NVLink -> fp32 partial
                 ev[3].record(side)
             self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)             # overlaps the combine gather
             main.wait_event(ev[3])
