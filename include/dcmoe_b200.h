@@ -173,9 +173,12 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
  * Combine.  Replaces core.py:486-488 + utils/UniMoE_Audio_utils.py:488-523 (decompress_matrix + "se,sem->sm"
  * einsum), core.py:338-353 (zeros + adds of routed and shared outputs): per token, a gather of the shared
  * row and of its <= n_real routed rows, fp32 accumulate in fixed order (deterministic, no atomics).
+ *   residual     [T, H] D or NULL: when given, out = D(residual + layer output), i.e. the decoder layer's residual add
+ *                (reference utils/UniMoE_Audio_model.py:242) is fused into the same pass (added last, in fp32)
  *   out          [T, H] D
  */
-int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out, void* stream);
+int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
+                  void* out, void* stream);
 
 /*
  * Weight packing (one-off, at load time): from the reference's separate gate_proj / up_proj / down_proj

@@ -84,7 +84,7 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         lib = _lib.load()
         c = m.dims.c_config(torch.float32)
-        rc = lib.dcmoe_combine(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, c, ctypes.c_void_p(16), None)
+        rc = lib.dcmoe_combine(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, c, None, ctypes.c_void_p(16), None)
         assert rc == -2 and b"no CPU fallback" in lib.dcmoe_last_error()
 
 

@@ -347,3 +347,79 @@ def test_cta_pair_ffn_matches_single_cta_ffn(B, S, dev):
     assert ((a - b).norm() / b.norm()).item() < 2e-3
     ref = O.forward(x.cpu(), W, None, logits=out2[1].cpu())
     _check_layer(out2[0].reshape(B * S, 2048), ref.final_hidden_states.reshape(B * S, 2048), dt)
+
+
+def test_stack_of_layers_chained_config3_shape(dev):
+    """BASELINE.json config 3 in miniature: several DCMoE layers with independent weights, activations chained
+    (RMS-normalised between layers as the decoder does before the MoE, model.py:239-241), one shared workspace.
+    Every layer is checked against the oracle on the activations it actually saw."""
+    dt = torch.bfloat16
+    T = 768
+    x = torch.randn(1, T, 2048, generator=torch.Generator().manual_seed(77)).to(dt).to(dev)
+    hidden = x
+    for layer_seed in (0, 1, 2):
+        m, W = _module(dt, dev, seed=layer_seed)
+        normed = (hidden.float() * torch.rsqrt(hidden.float().pow(2).mean(-1, keepdim=True) + 1e-6)).to(dt)
+        out = m(normed, None, None)
+        torch.cuda.synchronize()
+        ref = O.forward(normed.cpu(), W, None, logits=out[1].cpu())
+        assert torch.equal(out[3].cpu(), ref.expert_mask) and torch.equal(out[2].cpu(), ref.dynamic_top_k)
+        _check_layer(out[0].reshape(T, 2048), ref.final_hidden_states.reshape(T, 2048), dt)
+        hidden = hidden + out[0]                                    # residual (model.py:242)
+
+
+@pytest.mark.parametrize("top_p", [0.5, 0.95])
+def test_topp_sweep_with_skewed_router_config5_shape(top_p, dev):
+    """BASELINE.json config 5 in miniature: Top-P sweep with a skewed router (bias linspace(+2, -2) on the 9
+    dynamic logits -> hot expert 0), single GPU and 4 virtual expert-parallel ranks, against the oracle."""
+    from unimoe_audio_b200 import DCMoE
+    from unimoe_audio_b200.ep import LocalRanks
+    dt = torch.bfloat16
+    cfg = dict(O.DEFAULT_CONFIG, mlp_dynamic_top_p=top_p)
+    W = O.make_weights(seed=5, dtype=dt)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    m = m.to(dt).to_empty(device=dev).eval()
+    m.load_state_dict({k: v.to(dev) for k, v in W.items()})
+    T = 1024
+    gen = torch.Generator().manual_seed(int(top_p * 100))
+    x = torch.randn(1, T, 2048, generator=gen).to(dt)
+    logits = torch.randn(T, 11, generator=gen) * 0.9
+    logits[:, :9] += torch.linspace(2.0, -2.0, 9)
+    logits = logits.to(dt)
+    out = m(x.to(dev), None, None, router_logits=logits.to(dev))
+    torch.cuda.synchronize()
+    ref = O.forward(x, W, None, cfg=cfg, logits=logits)
+    assert torch.equal(out[2].cpu(), ref.dynamic_top_k) and torch.equal(out[3].cpu(), ref.expert_mask)
+    assert torch.equal(out[4].cpu(), ref.global_weight)
+    counts = m.last_workspace.counts.cpu().long()
+    assert torch.equal(counts, ref.counts.long())
+    assert counts[0] > 2 * counts[7]                                  # the skew really loads expert 0
+    _check_layer(out[0].reshape(T, 2048), ref.final_hidden_states.reshape(T, 2048), dt)
+    # 4 expert-parallel virtual ranks on the same tokens (router fed the same logits slices)
+    lr = LocalRanks(m, 4)
+    xs = [x[:, r * 256:(r + 1) * 256].to(dev).contiguous() for r in range(4)]
+    for r, ep in enumerate(lr.ranks):
+        ep._forced_logits = logits[r * 256:(r + 1) * 256].to(dev).contiguous()
+    outs = lr.forward(xs)
+    torch.cuda.synchronize()
+    got = torch.cat([o[0][0] for o in outs])
+    assert torch.equal(got, out[0][0])
+
+
+def test_fused_residual_add(dev):
+    """`residual=` fuses the decoder layer's `residual + mlp(...)` (model.py:242) into the combine pass."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=1)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 200, 2048, generator=gen).to(dt).to(dev)
+    res = torch.randn(2, 200, 2048, generator=gen).to(dt).to(dev)
+    plain = m(x, None, None)
+    fused = m(x, None, None, residual=res)
+    torch.cuda.synchronize()
+    expect = (res.float() + plain[0].float())
+    # fused adds in fp32 before the single rounding: at least as close to the fp32 sum as rounding the layer first
+    err_fused = (fused[0].float() - expect).abs().max().item()
+    err_plain = ((res + plain[0]).float() - expect).abs().max().item()
+    assert err_fused <= err_plain + 1e-6 and err_fused <= 2e-2
+    assert torch.equal(fused[3], plain[3])

@@ -26,12 +26,12 @@ def main():
         for _, p in sorted(m.named_parameters(), key=lambda kv: kv[0]):
             p.copy_((torch.randn(p.shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt))
     print("weights per layer: 304.4 MB bf16 -> %.1f us at 6.53 TB/s (floor when every expert is hit)" % (304.4e6 / 6.5297e12 * 1e6))
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     for T in (2, 8, 32, 128, 512):
         x = torch.randn(T, 1, 2048, generator=gen, device=dev, dtype=torch.float32).to(dt)
         for _ in range(5):
             m(x, None, None)
         torch.cuda.synchronize()
-        n = 200
         t0 = time.perf_counter()
         for _ in range(n):
             m(x, None, None)

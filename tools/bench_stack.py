@@ -1,0 +1,88 @@
+"""BASELINE.json configs[2]: full decoder stack prefill (36 layers, random init), batch 16 x 4096 tokens on one B200.
+Only the MoE layers are ours; attention (torch SDPA, GQA 16/2 heads) and RMSNorm just feed realistic activations.
+Reports the summed MoE time (CUDA events around every DCMoE forward) and tokens/s through the 36 MoE layers.
+
+    python tools/bench_stack.py [--layers 36] [--batch 16] [--seq 4096]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from unimoe_audio_b200 import DCMoE  # noqa: E402
+
+CFG = dict(hidden_size=2048, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
+           mlp_dynamic_top_k=0.0, mlp_fixed_expert_num=2, dynamic_intermediate_size=2752,
+           shared_intermediate_size=1376, router_jitter_noise=0.01)
+
+
+def rms(x, eps=1e-6):
+    xf = x.float()
+    return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=36)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--seq", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16
+    layers, attn = [], []
+    for L in range(a.layers):
+        with torch.device("meta"):
+            m = DCMoE(CFG)
+        m = m.to(dt).to_empty(device=dev).eval()
+        gen = torch.Generator(device=dev).manual_seed(L)
+        with torch.no_grad():
+            for _, p in sorted(m.named_parameters(), key=lambda kv: kv[0]):
+                p.copy_((torch.randn(p.shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt))
+        m.release_reference_weights()
+        layers.append(m)
+        attn.append({k: (torch.randn(s, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt)
+                     for k, s in (("q", (2048, 2048)), ("k", (256, 2048)), ("v", (256, 2048)), ("o", (2048, 2048)))})
+    B, S = a.batch, a.seq
+    h0 = torch.randn(B, S, 2048, generator=torch.Generator(device=dev).manual_seed(1236), device=dev, dtype=torch.float32).to(dt)
+    best = None
+    for rep in range(a.reps + 1):
+        h = h0.clone()
+        evs = []
+        for L in range(a.layers):
+            w = attn[L]
+            xn = rms(h)
+            q = F.linear(xn, w["q"]).view(B, S, 16, 128).transpose(1, 2)
+            k = F.linear(xn, w["k"]).view(B, S, 2, 128).transpose(1, 2)
+            v = F.linear(xn, w["v"]).view(B, S, 2, 128).transpose(1, 2)
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
+            h = h + F.linear(o.transpose(1, 2).reshape(B, S, 2048), w["o"])
+            xn = rms(h)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = layers[L](xn, None, None)
+            e.record()
+            evs.append((s, e))
+            h = h + out[0]
+        torch.cuda.synchronize()
+        per_layer = [s.elapsed_time(e) for s, e in evs]
+        if rep > 0 and (best is None or sum(per_layer) < sum(best)):
+            best = per_layer
+        ws = layers[-1].last_workspace
+    T = B * S
+    rows = int(ws.mtiles[: int(ws.n_mtiles.item()), 3].sum().item())
+    res = {"config": f"configs[2]: {a.layers}-layer stack prefill, batch {B} x {S} tokens, bf16, 1 x B200",
+           "moe_ms_total": sum(best), "moe_ms_per_layer_mean": sum(best) / len(best), "moe_ms_per_layer_min": min(best),
+           "moe_ms_per_layer_max": max(best), "tokens_per_s_through_moe_layers": T * a.layers / (sum(best) * 1e-3),
+           "ffn_rows_last_layer": rows, "mean_routed_experts_last_layer": (rows - T) / T,
+           "finite": bool(torch.isfinite(h.float()).all().item())}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

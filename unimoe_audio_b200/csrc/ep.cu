@@ -237,7 +237,7 @@ template <bool BF16, int MODE>
 __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restrict__ y_local, EpPeers peers,
                                                             const int32_t* __restrict__ slot_of, int64_t T, int H,
                                                             int n_real, int n_loc, float* __restrict__ partial,
-                                                            char* __restrict__ out) {
+                                                            const char* __restrict__ residual, char* __restrict__ out) {
     constexpr int ESIZE = BF16 ? 2 : 4;
     constexpr int PER = 16 / ESIZE;
     constexpr int U = 4;             // 128-bit vectors per lane per pass (x 2 source rows in flight)
@@ -337,6 +337,16 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
                         make_float4(acc[u][4 * q], acc[u][4 * q + 1], acc[u][4 * q + 2], acc[u][4 * q + 3]);
             }
         } else {
+            if (residual != nullptr) {                 // fused residual add of the decoder layer (model.py:242), added last
+                uint4 rv[U];
+                const uint4* rs = reinterpret_cast<const uint4*>(residual + t * row_bytes);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    rv[u] = c < n_vec ? ld_nc_v4(rs + c) : make_uint4(0, 0, 0, 0);
+                }
+                add(acc, rv);
+            }
             uint4* dst = reinterpret_cast<uint4*>(out + t * row_bytes);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -362,18 +372,19 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
 }  // namespace
 
 // single-GPU combine = the expert-parallel combine with one rank (peers.y[0] = y)
-int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, void* out,
-                   cudaStream_t stream) {
+int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
+                   void* out, cudaStream_t stream) {
     if (T == 0) return DCMOE_OK;
     EpPeers peers{};
     peers.y[0] = (const char*)y;
     dim3 grid((unsigned)ceil_div(T, 8)), block(256);
     if (cfg->dtype == DCMOE_BF16)
         ep_combine_kernel<true, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
-                                                               cfg->n_real, cfg->n_real, nullptr, (char*)out);
+                                                               cfg->n_real, cfg->n_real, nullptr, (const char*)residual, (char*)out);
     else
         ep_combine_kernel<false, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
-                                                                cfg->n_real, cfg->n_real, nullptr, (char*)out);
+                                                                cfg->n_real, cfg->n_real, nullptr, (const char*)residual,
+                                                                (char*)out);
     return check_cuda(cudaGetLastError(), "combine kernel launch");
 }
 
@@ -485,7 +496,7 @@ int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32
     const bool bf16 = cfg->dtype == DCMOE_BF16;
 #define DCMOE_EP_COMBINE(BF, MODE_)                                                                                   \
     ep_combine_kernel<BF, MODE_><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)y_local, peers, slot_of, T,  \
-        cfg->hidden_size, cfg->n_real, cfg->n_real / world, partial, (char*)out)
+        cfg->hidden_size, cfg->n_real, cfg->n_real / world, partial, nullptr, (char*)out)
     if (mode == 0) { if (bf16) DCMOE_EP_COMBINE(true, 0); else DCMOE_EP_COMBINE(false, 0); }
     else if (mode == 1) { if (bf16) DCMOE_EP_COMBINE(true, 1); else DCMOE_EP_COMBINE(false, 1); }
     else { if (bf16) DCMOE_EP_COMBINE(true, 2); else DCMOE_EP_COMBINE(false, 2); }

@@ -153,6 +153,7 @@ class DCMoE(nn.Module):
         self.row_capacity = 0             # 0 = worst case
         self.last_workspace: Optional[Workspace] = None
         self.stage_hook = None            # optional callable(stage_name) invoked between kernel launches (bench)
+        self._reference_released = False
 
     # ------------------------------------------------------------------ weights
     @classmethod
@@ -185,6 +186,8 @@ class DCMoE(nn.Module):
     def pack_weights(self, force: bool = False):
         """(Re)build W13 [n_real+1, 2*I_d, H] (gate/up rows interleaved in blocks of 64) and
         W2 [n_real+1, H, I_d]; group n_real is the shared-expert pack (2 x I_s = I_d)."""
+        if self._w13 is not None and self._reference_released:
+            return
         p = self.gate.weight
         routed, shared = self._expert_params()
         key = (p.device, p.dtype, tuple(w._version for m in list(routed) + list(shared)
@@ -205,11 +208,21 @@ class DCMoE(nn.Module):
                             m.down_proj.weight.detach().contiguous(), d.n_real, i, d, w13, w2)
         self._w13, self._w2, self._packed_key = w13, w2, key
 
+    def release_reference_weights(self):
+        """Free the per-expert gate/up/down parameters after packing (halves the weight memory of a layer: the
+        kernels only read the packed W13 / W2).  The state dict can no longer be saved from this module."""
+        self.pack_weights()
+        routed, shared = self._expert_params()
+        for m in list(routed) + list(shared):
+            for lin in (m.gate_proj, m.up_proj, m.down_proj):
+                lin.weight.data = torch.empty(0, dtype=lin.weight.dtype, device=lin.weight.device)
+        self._reference_released = True
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                aux_balance_weight: Optional[torch.Tensor] = None, router_logits: Optional[torch.Tensor] = None
-                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                aux_balance_weight: Optional[torch.Tensor] = None, router_logits: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         if self.training:
             raise NotImplementedError("DCMoE implements the inference forward (eval mode); training-only branches "
                                       "(fp32 gate, jitter, gumbel routing: core.py:240-249, :111-135) are out of scope")
@@ -250,7 +263,14 @@ class DCMoE(nn.Module):
             hook("ffn_gemm1")
             ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)
             hook("ffn_gemm2")
-            ops.combine(ws, out)
+            res = None
+            if residual is not None:      # extension: fuse the decoder layer's residual add (model.py:242)
+                if residual.shape != hidden_states.shape or residual.dtype != dt:
+                    raise ValueError("residual must match hidden_states in shape and dtype")
+                res = residual.reshape(T, H)
+                if not res.is_contiguous():
+                    res = res.contiguous()
+            ops.combine(ws, out, res)
             hook("combine")
         aux = ws.aux_loss.clone().reshape(())
         return out, logits, top_k, mask, gw, aux

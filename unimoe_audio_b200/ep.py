@@ -198,6 +198,8 @@ class ExpertParallelDCMoE:
         hook("start")
         wg = m.gate.weight.detach()
         self._x = x
+        if router_logits is None:
+            router_logits = getattr(self, "_forced_logits", None)     # tests: identical logits on every path
         self._route = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
         hook("router")
         ops.plan(ws)                     # local counts + block prefix sums (+ local aux loss)

@@ -152,9 +152,9 @@ def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Worksp
                                      impl, phase, _stream()), "dcmoe_grouped_ffn")
 
 
-def combine(ws: Workspace, out: torch.Tensor):
+def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] = None):
     lib = _lib.load()
-    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(out), _stream()),
+    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(residual), _ptr(out), _stream()),
                "dcmoe_combine")
 
 
