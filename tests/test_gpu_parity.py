@@ -423,3 +423,20 @@ def test_fused_residual_add(dev):
     err_plain = ((res + plain[0]).float() - expect).abs().max().item()
     assert err_fused <= err_plain + 1e-6 and err_fused <= 2e-2
     assert torch.equal(fused[3], plain[3])
+
+
+@pytest.mark.parametrize("B,S", [(2, 1), (1, 8), (3, 11)])
+def test_experimental_decode_ffn_kernels(B, S, dev):
+    """impl = 3 (weights as the mma.sync M operand, T <= 64) against the default tcgen05 path."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=2)
+    x = torch.randn(B, S, 2048, generator=torch.Generator().manual_seed(5 + S)).to(dt).to(dev)
+    m.ffn_impl = 0
+    ref = [t.clone() for t in m(x, None, None)]
+    m.ffn_impl = 3
+    out = m(x, None, None)
+    torch.cuda.synchronize()
+    m.ffn_impl = None
+    a, b = out[0].float(), ref[0].float()
+    assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
+    assert ((a - b).norm() / b.norm()).item() < 3e-3

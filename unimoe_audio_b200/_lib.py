@@ -31,7 +31,7 @@ class DcmoeSizes(Structure):
 
 class DcmoePlanLayout(Structure):
     _fields_ = [(n, c_int64) for n in ("block_counts", "block_probs", "block_offsets", "counts", "seg_base",
-                                       "n_mtiles", "aux_loss", "mtiles", "n_pairs", "pairs", "total")]
+                                       "n_mtiles", "aux_loss", "mtiles", "overflow", "n_pairs", "pairs", "total")]
 
 
 class DcmoeError(RuntimeError):

@@ -124,6 +124,7 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     l->n_mtiles = off;     off = align_up(off + 4, 16);
     l->aux_loss = off;     off = align_up(off + 4, 16);
     l->mtiles = off;       off = align_up(off + sz->max_mtiles * (int64_t)sizeof(dcmoe_mtile), 16);
+    l->overflow = off;     off = align_up(off + 4, 16);
     l->n_pairs = off;      off = align_up(off + 4, 16);
     l->pairs = off;        off = align_up(off + sz->max_mtiles * 4, 16);
     l->total = off;
@@ -144,6 +145,8 @@ int launch_ffn_simt(const void*, const void*, const void*, const void*, const fl
                     const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                        const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+int launch_ffn_decode(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
+                      const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
 int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                             const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 
@@ -247,6 +250,8 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     // 1 shared-expert tiles only, 2 routed tiles only)
     const int group_sel = (phase >> 4) & 3;
     const int max_ctas = (phase >> 8) & 0xfff;   // bits 8-19: cap on the persistent grid (0 = one CTA per SM)
+    const bool no_decode = (phase >> 20) & 1;    // bit 20: never pick the decode kernels (expert parallelism: a rank
+                                                 // can own more rows than it has tokens)
     phase &= 15;
     DCMOE_PROLOGUE(T)
     if (T > 0 && (!x || !x_packed || !w13 || !w2 || !row_scale || !plan || !h || !y)) {
@@ -256,6 +261,12 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     if (phase < 0 || phase > 2) { set_error("dcmoe_grouped_ffn: phase must be 0, 1 or 2"); return DCMOE_ERR_INVALID; }
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
+    (void)no_decode;
+    if (impl == 3) {
+        // experimental decode kernels (weights as the mma.sync M operand).  Measured equal to the tcgen05 path at
+        // T = 2 (65 us for both GEMMs) and slower from T = 16 up, so they are never selected automatically.
+        return launch_ffn_decode(x, x_packed, w13, w2, row_scale, T, cfg, sz, pv, h, y, phase, (cudaStream_t)stream);
+    }
     if (impl == 2) {
         if (cfg->dtype != DCMOE_BF16) { set_error("tcgen05 FFN is bf16 only"); return DCMOE_ERR_INVALID; }
         return launch_ffn_tcgen05_2cta(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase, group_sel,

@@ -34,6 +34,7 @@ struct PlanView {
     int32_t* n_mtiles;
     float* aux_loss;
     dcmoe_mtile* mtiles;
+    int32_t* overflow;
     int32_t* n_pairs;
     int32_t* pairs;
 };
@@ -49,6 +50,7 @@ inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
     v.n_mtiles = reinterpret_cast<int32_t*>(p + l.n_mtiles);
     v.aux_loss = reinterpret_cast<float*>(p + l.aux_loss);
     v.mtiles = reinterpret_cast<dcmoe_mtile*>(p + l.mtiles);
+    v.overflow = reinterpret_cast<int32_t*>(p + l.overflow);
     v.n_pairs = reinterpret_cast<int32_t*>(p + l.n_pairs);
     v.pairs = reinterpret_cast<int32_t*>(p + l.pairs);
     return v;

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) ep_plan_kernel(const int32_t* __restrict_
         s_tile0[n_loc] = tile;
         pv.seg_base[n_loc] = row;
         *pv.n_mtiles = tile < max_mtiles ? tile : max_mtiles;
+        *pv.overflow = tile > max_mtiles ? 1 : 0;   // only possible when the caller chose a row_capacity below the worst case
     }
     __syncthreads();
     const int n_shared_tiles = t_pad / kTileM;

@@ -73,6 +73,8 @@ struct GemmParams {
     const dcmoe_mtile* mtiles;
     const int32_t* n_mtiles;
     const float* row_scale;
+    int bn;             // accumulator columns per tile: 256, or 128 for small token counts (more, finer tiles so
+                        // that every SM streams weights when the layer is weight-bandwidth bound)
     int m_begin;        // first m-tile of this launch
     int m_end;          // one past the last m-tile; < 0: read *n_mtiles
 };
@@ -133,12 +135,12 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
             const int nt = tile % p.n_tiles;
             const CUtensorMap* amap = SWIGLU ? (mt.group == p.n_real ? &tmap_a0 : &tmap_a1) : &tmap_a0;
             const int a_row = SWIGLU ? mt.a_row : mt.out_row;
-            const int b_row = mt.group * p.w_rows + nt * BN;
+            const int b_row = mt.group * p.w_rows + nt * p.bn;
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
                     const uint32_t a_dst = smem_base + stage * STAGE_BYTES;
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    mbar_expect_tx(full_bar(stage), (uint32_t)(A_BYTES + p.bn * BK * 2));
                     tma_load_2d(a_dst, amap, kb * BK, a_row, full_bar(stage));
                     tma_load_2d(a_dst + A_BYTES, &tmap_b, kb * BK, b_row, full_bar(stage));
                 }
@@ -152,7 +154,7 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
         uint32_t phase = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
-            const uint32_t idesc = make_idesc(nt == p.n_tiles - 1 ? p.n_last : BN);
+            const uint32_t idesc = make_idesc(nt == p.n_tiles - 1 ? p.n_last : p.bn);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -185,7 +187,7 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const dcmoe_mtile mt = p.mtiles[p.m_begin + tile / p.n_tiles];
             const int nt = tile % p.n_tiles;
-            const int n_acc = nt == p.n_tiles - 1 ? p.n_last : BN;
+            const int n_acc = nt == p.n_tiles - 1 ? p.n_last : p.bn;
             const int n_chunks = SWIGLU ? n_acc / 128 : n_acc / 64;
             float sa = 1.0f, sb = 1.0f;
             if (SWIGLU) {
@@ -209,7 +211,7 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
                         tmem_ld32(t_row + (uint32_t)(128 * j + 32 * hf), g);
                         tmem_ld32(t_row + (uint32_t)(128 * j + 64 + 32 * hf), u);
                         tmem_ld_wait();
-                        const int hcol0 = nt * (BN / 2) + 64 * j + 32 * hf;
+                        const int hcol0 = nt * (p.bn / 2) + 64 * j + 32 * hf;
                         const float sc = (shared_grp && hcol0 >= p.split_col) ? sb : sa;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -238,7 +240,7 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    const int col0 = SWIGLU ? nt * (BN / 2) + 64 * j : nt * BN + 64 * j;
+                    const int col0 = SWIGLU ? nt * (p.bn / 2) + 64 * j : nt * p.bn + 64 * j;
                     tma_store_2d(&tmap_out, slab, col0, mt.out_row + wq * 32);
                     tma_commit_group();
                 }
@@ -300,15 +302,18 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     const int64_t packed_rows = row_capacity - sz.t_pad;
     if ((rc = make_tensor_map_bf16(&m_x, x, T, H, BM))) return rc;
     if ((rc = make_tensor_map_bf16(&m_xp, x_packed, packed_rows > 0 ? packed_rows : 1, H, BM))) return rc;
-    if ((rc = make_tensor_map_bf16(&m_w13, w13, (int64_t)G * 2 * Id, H, BN))) return rc;
+    const int bn = BN;   // (128-column tiles were measured for decode sizes: slower -- the 128-row A tile then is
+                         // half of every stage's bytes; decode sizes use ffn_decode.cu instead)
+    if ((rc = make_tensor_map_bf16(&m_w13, w13, (int64_t)G * 2 * Id, H, bn))) return rc;
     if ((rc = make_tensor_map_bf16(&m_h_st, h, row_capacity, Id, 32))) return rc;
     if ((rc = make_tensor_map_bf16(&m_h_ld, h, row_capacity, Id, BM))) return rc;
-    if ((rc = make_tensor_map_bf16(&m_w2, w2, (int64_t)G * H, Id, BN))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_w2, w2, (int64_t)G * H, Id, bn))) return rc;
     if ((rc = make_tensor_map_bf16(&m_y_st, y, row_capacity, H, 32))) return rc;
 
     GemmParams p1, p2;
-    p1.n_tiles = (int)ceil_div(2 * Id, BN);
-    p1.n_last = 2 * Id - (p1.n_tiles - 1) * BN;
+    p1.bn = bn;
+    p1.n_tiles = (int)ceil_div(2 * Id, bn);
+    p1.n_last = 2 * Id - (p1.n_tiles - 1) * bn;
     p1.num_kb = H / BK;
     p1.w_rows = 2 * Id;
     p1.n_real = cfg->n_real;
@@ -321,8 +326,8 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     p1.m_begin = group_sel == 2 ? n_shared_tiles : 0;
     p1.m_end = group_sel == 1 ? n_shared_tiles : -1;
     p2 = p1;
-    p2.n_tiles = (int)ceil_div(H, BN);
-    p2.n_last = H - (p2.n_tiles - 1) * BN;
+    p2.n_tiles = (int)ceil_div(H, bn);
+    p2.n_last = H - (p2.n_tiles - 1) * bn;
     p2.num_kb = Id / BK;
     p2.w_rows = H;
 

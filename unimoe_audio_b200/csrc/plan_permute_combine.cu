@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         s_tile0[n_real] = tile;
         pv.seg_base[n_real] = row;
         *pv.n_mtiles = tile < max_mtiles ? tile : max_mtiles;
+        *pv.overflow = tile > max_mtiles ? 1 : 0;   // only possible when the caller chose a row_capacity below the worst case
         double acc = 0.0;
         for (int j = 0; j < n_dyn; ++j) acc += s_term[j];         // fixed left-to-right order over experts
         *pv.aux_loss = (float)acc * (float)n_dyn;

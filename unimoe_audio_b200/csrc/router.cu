@@ -763,14 +763,17 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
                                                            logits_out, top_k, expert_mask, global_weight,            \
                                                            block_counts, block_probs)
     const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
-    static int ws_mode = -1;
-    if (ws_mode < 0) {
+    static int ws_mode_env = -1;
+    if (ws_mode_env < 0) {
         const char* env = getenv("DCMOE_ROUTER_MODE");   // debug switch: 0 = one CTA per block, 1 = warp-specialised
-        ws_mode = env ? atoi(env) : 2;                   // (register-staged loads), 2 = TMA-fed persistent (default)
+        ws_mode_env = env ? atoi(env) : 2;               // (register-staged loads), 2 = TMA-fed persistent (default)
     }
+    int ws_mode = ws_mode_env;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // (decode-sized calls were measured with the one-CTA-per-block kernel too: 21.8 us vs 14.7 us for the TMA-fed
+    // kernel at T = 2, so the persistent kernel is used at every size)
     if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0) {
         static bool attr_done = false;
         if (!attr_done) {

@@ -245,7 +245,7 @@ class ExpertParallelDCMoE:
         _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
                                          self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, self._local_cfg,
                                          ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl,
-                                         phase | (group_sel << 4) | (max_ctas << 8), st),
+                                         phase | (group_sel << 4) | (max_ctas << 8) | (1 << 20), st),
                    "dcmoe_grouped_ffn")
         if name and self.m.stage_hook:
             self.m.stage_hook(name)

@@ -100,6 +100,12 @@ class Workspace:
         return self._view(self.layout.n_mtiles, 1, torch.int32)
 
     @property
+    def overflowed(self) -> bool:
+        """True if the last plan did not fit `row_capacity` (rows were dropped).  Reading it synchronises; the
+        default worst-case capacity can never overflow."""
+        return bool(self._view(self.layout.overflow, 1, torch.int32).item())
+
+    @property
     def aux_loss(self) -> torch.Tensor:
         return self._view(self.layout.aux_loss, 1, torch.float32)
 
