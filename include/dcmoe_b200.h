@@ -136,6 +136,16 @@ int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const
 int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* plan, void* stream);
 
 /*
+ * Decode front end: dcmoe_router + dcmoe_plan + dcmoe_permute in one single-CTA launch for T <= 64 tokens (bf16):
+ * the generation loop (reference model.py:1149-1203) calls the layer with a handful of tokens, where the three
+ * launches are pure latency.  Same outputs, bit for bit (the block_counts / block_probs / block_offsets scratch
+ * sections of the plan are not written).
+ */
+int dcmoe_front_small(const void* x, const void* w_gate, const int32_t* attn_mask, int64_t T, int64_t row_capacity,
+                      const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight,
+                      void* plan, void* x_packed, int32_t* slot_of, int32_t* row_token, float* row_scale, void* stream);
+
+/*
  * Permute (dispatch).  Replaces core.py:459-462 + utils/UniMoE_Audio_utils.py:436-485
  * (compress_matrix x2 + the 0/1 "ce,cem->ecm" einsum): rows of x are gathered into the packed
  * routed part of row space with 128-bit loads/stores.

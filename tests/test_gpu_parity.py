@@ -440,3 +440,43 @@ def test_experimental_decode_ffn_kernels(B, S, dev):
     a, b = out[0].float(), ref[0].float()
     assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
     assert ((a - b).norm() / b.norm()).item() < 3e-3
+
+
+@pytest.mark.parametrize("T,masked", [(1, False), (2, False), (17, True), (64, False), (33, True)])
+def test_fused_decode_front_end_equals_three_kernel_path(T, masked, dev):
+    """dcmoe_front_small (router + plan + permute in one launch, T <= 64) must reproduce the three-kernel path bit
+    for bit: routing outputs, counts, segment bases, tile table, pairs, slots, scales, gathered rows, aux."""
+    from unimoe_audio_b200 import ops
+    dt = torch.bfloat16
+    gen = torch.Generator().manual_seed(900 + T)
+    x = torch.randn(T, 2048, generator=gen).to(dt).to(dev)
+    wg = (torch.randn(11, 2048, generator=gen) * 0.02).to(dt).to(dev)
+    am = (torch.rand(T, generator=gen) > 0.3).to(dev) if masked else None
+    ws_a = ops.Workspace(_dims(), dt, T, dev)
+    ws_b = ops.Workspace(_dims(), dt, T, dev)
+    ra = ops.router(x, wg, ws_a, attention_mask=am)
+    ops.plan(ws_a)
+    ops.permute(x, ra[2], ra[3], ws_a)
+    rb = ops.front_small(x, wg, ws_b, attention_mask=am)
+    torch.cuda.synchronize()
+    for a, b in zip(ra, rb):
+        assert torch.equal(a, b)
+    assert torch.equal(ws_a.counts, ws_b.counts) and torch.equal(ws_a.seg_base, ws_b.seg_base)
+    n = ws_a.n_mtiles.item()
+    assert n == ws_b.n_mtiles.item() and torch.equal(ws_a.mtiles[:n], ws_b.mtiles[:n])
+    la, lb = ws_a.layout, ws_b.layout
+    npa = ws_a._view(la.n_pairs, 1, torch.int32).item()
+    assert npa == ws_b._view(lb.n_pairs, 1, torch.int32).item()
+    assert torch.equal(ws_a._view(la.pairs, npa, torch.int32), ws_b._view(lb.pairs, npa, torch.int32))
+    assert torch.equal(ws_a.slot_of, ws_b.slot_of)
+    used = int(ws_a.seg_base[-1].item())
+    valid = torch.zeros(used, dtype=torch.bool, device=dev)
+    mt = ws_a.mtiles[:n]
+    for i in range(n):
+        valid[mt[i, 1].item(): mt[i, 1].item() + mt[i, 3].item()] = True
+    assert torch.equal(ws_a.row_token[:used][valid], ws_b.row_token[:used][valid])
+    assert torch.equal(ws_a.row_scale[:used][valid], ws_b.row_scale[:used][valid])
+    t_pad = ws_a.t_pad
+    routed = valid[t_pad:]
+    assert torch.equal(ws_a.x_packed[: used - t_pad][routed], ws_b.x_packed[: used - t_pad][routed])
+    assert torch.equal(ws_a.aux_loss, ws_b.aux_loss) or abs(ws_a.aux_loss.item() - ws_b.aux_loss.item()) <= 1e-6 * abs(ws_a.aux_loss.item())

@@ -47,6 +47,8 @@ SIGNATURES = {
     "dcmoe_query_sizes": (c_int, [POINTER(DcmoeConfig), c_int64, c_int64, POINTER(DcmoeSizes), POINTER(DcmoePlanLayout)]),
     "dcmoe_router": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dcmoe_front_small": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dcmoe_plan": (c_int, [c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p]),
     "dcmoe_permute": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -136,6 +136,8 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
 int launch_router(const void*, const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, void*, int64_t*,
                   int32_t*, void*, int32_t*, float*, cudaStream_t);
 int launch_plan(int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView, cudaStream_t);
+int launch_front_small(const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
+                       void*, int64_t*, int32_t*, void*, void*, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_permute(const void*, const int32_t*, const void*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
                    void*, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, const void*, void*, cudaStream_t);
@@ -219,6 +221,21 @@ static int plan_for(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, vo
     if (rc) return rc;
     *pv = plan_view(plan, l);
     return DCMOE_OK;
+}
+
+int dcmoe_front_small(const void* x, const void* w_gate, const int32_t* attn_mask, int64_t T, int64_t row_capacity,
+                      const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight,
+                      void* plan, void* x_packed, int32_t* slot_of, int32_t* row_token, float* row_scale, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!x || !w_gate || !logits_out || !top_k || !expert_mask || !global_weight || !plan || !x_packed || !slot_of ||
+                  !row_token || !row_scale)) {
+        set_error("dcmoe_front_small: NULL pointer argument");
+        return DCMOE_ERR_INVALID;
+    }
+    dcmoe_sizes sz; PlanView pv;
+    if ((rc = plan_for(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
+    return launch_front_small(x, w_gate, attn_mask, T, cfg, sz, pv, logits_out, top_k, expert_mask, global_weight, x_packed,
+                              slot_of, row_token, row_scale, (cudaStream_t)stream);
 }
 
 int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* plan, void* stream) {

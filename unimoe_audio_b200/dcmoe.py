@@ -154,6 +154,7 @@ class DCMoE(nn.Module):
         self.last_workspace: Optional[Workspace] = None
         self.stage_hook = None            # optional callable(stage_name) invoked between kernel launches (bench)
         self._reference_released = False
+        self.use_front_small = True       # T <= 64 (bf16): fused router + plan + permute launch
 
     # ------------------------------------------------------------------ weights
     @classmethod
@@ -251,13 +252,19 @@ class DCMoE(nn.Module):
         hook = self.stage_hook or (lambda _name: None)
         out = torch.empty((B, S, H), dtype=dt, device=x.device)
         hook("start")
-        logits, top_k, mask, gw = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
-        hook("router")
-        ops.plan(ws)
-        hook("plan")
+        small = (dt == torch.bfloat16 and 0 < T <= 64 and router_logits is None and self.use_front_small)
+        if small:     # decode-sized call: router + plan + permute in one single-CTA launch
+            logits, top_k, mask, gw = ops.front_small(x, wg, ws, attention_mask=attention_mask)
+            hook("front_small")
+        else:
+            logits, top_k, mask, gw = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
+            hook("router")
+            ops.plan(ws)
+            hook("plan")
         if T > 0:
-            ops.permute(x, mask, gw, ws)
-            hook("permute")
+            if not small:
+                ops.permute(x, mask, gw, ws)
+                hook("permute")
             impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
             ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
             hook("ffn_gemm1")

@@ -139,6 +139,26 @@ def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Worksp
     return logits, top_k, mask, gw
 
 
+def front_small(x: torch.Tensor, w_gate: torch.Tensor, ws: Workspace, attention_mask: Optional[torch.Tensor] = None):
+    """router + plan + permute in one launch (bf16, T <= 64).  Returns what ``router`` returns."""
+    lib = _lib.load()
+    dims, T, dt, dev = ws.dims, ws.T, ws.dtype, ws.device
+    E = dims.n_experts
+    logits = torch.empty((T, E), dtype=dt, device=dev)
+    top_k = torch.empty((T,), dtype=torch.int64, device=dev)
+    mask = torch.empty((T, E), dtype=torch.int32, device=dev)
+    gw = torch.empty((T, E), dtype=dt, device=dev)
+    am = None
+    if attention_mask is not None:
+        am = attention_mask.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+        if am.numel() != T:
+            raise ValueError("attention_mask must have one entry per token")
+    _lib.check(lib.dcmoe_front_small(_ptr(x), _ptr(w_gate), _ptr(am), T, ws.row_capacity, ws.cfg, _ptr(logits), _ptr(top_k),
+                                     _ptr(mask), _ptr(gw), _ptr(ws.plan), _ptr(ws.x_packed), _ptr(ws.slot_of),
+                                     _ptr(ws.row_token), _ptr(ws.row_scale), _stream()), "dcmoe_front_small")
+    return logits, top_k, mask, gw
+
+
 def plan(ws: Workspace):
     lib = _lib.load()
     _lib.check(lib.dcmoe_plan(ws.T, ws.row_capacity, ws.cfg, _ptr(ws.plan), _stream()), "dcmoe_plan")
