@@ -454,10 +454,15 @@ def test_fused_decode_front_end_equals_three_kernel_path(T, masked, dev):
     am = (torch.rand(T, generator=gen) > 0.3).to(dev) if masked else None
     ws_a = ops.Workspace(_dims(), dt, T, dev)
     ws_b = ops.Workspace(_dims(), dt, T, dev)
-    ra = ops.router(x, wg, ws_a, attention_mask=am)
+    rb = ops.front_small(x, wg, ws_b, attention_mask=am)
+    # the gate projection splits K differently in the two kernels (fp32 partial sums in another order), so the
+    # logits may differ by one bf16 ulp: compare them with a tolerance and run the three-kernel path on the front
+    # end's logits -- everything downstream must then be identical
+    r0 = ops.router(x, wg, ws_a, attention_mask=am)
+    assert (r0[0].float() - rb[0].float()).abs().max().item() <= 2e-2
+    ra = ops.router(None, None, ws_a, logits_in=rb[0], attention_mask=am)
     ops.plan(ws_a)
     ops.permute(x, ra[2], ra[3], ws_a)
-    rb = ops.front_small(x, wg, ws_b, attention_mask=am)
     torch.cuda.synchronize()
     for a, b in zip(ra, rb):
         assert torch.equal(a, b)
