@@ -234,6 +234,13 @@ def run_ours(args):
     barrier()
 
     m.stage_hook = hook
+    for i in range(2):           # untimed steps with the event hooks on (first-use costs of the hook path stay outside)
+        stage_events.append([])
+        layer(xs[i % n_rot], None, None)
+    barrier()
+    stage_events.clear()
+    if world > 1 and hasattr(layer, "comm_events"):
+        layer.comm_events.clear()
     if rank == 0:
         sampler.mark_begin()
     step_ev = []
@@ -265,6 +272,12 @@ def run_ours(args):
         for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
             stages.setdefault(n1, []).append(e0.elapsed_time(e1))
     stage_ms = {k: statistics.median(v) for k, v in stages.items()}   # median: robust to a host hiccup in one step
+    comm_ms = {}
+    if world > 1 and getattr(layer, "comm_events", None):
+        acc = {}
+        for name, a, b in layer.comm_events:
+            acc.setdefault(name, []).append(a.elapsed_time(b))
+        comm_ms = {k: statistics.median(v) for k, v in acc.items()}
 
     # routed rows of the last step (A = sum_t r_t) -> algorithmic FLOPs of the grouped GEMMs
     ws = m.last_workspace
@@ -306,6 +319,19 @@ def run_ours(args):
         if g2_key in stage_ms:
             roofline["gemm2"] = {"achieved": g1_rows * FLOP_PER_ROW_GEMM2 / (stage_ms[g2_key] * 1e-3) / 1e12,
                                  "unit": "TFLOP/s", "ms": stage_ms[g2_key], "launch": g2_key}
+
+    if world > 1 and roofline is not None:
+        # expert-parallel exchange: rows that leave this rank (dispatch) / come back (combine gather), 4096 B each,
+        # against the measured peer-copy bandwidth of this pool (B200_PROFILING.md: 770 GB/s per direction per GPU)
+        A_sent = int(out[3][:, :8].sum().item())
+        remote = A_sent * (world - 1) / world
+        nv = {}
+        for key, name in (("ep_dispatch", "dispatch"), ("ep_combine_gather", "combine_gather"), ("ep_combine", "combine")):
+            ms = comm_ms.get(key, stage_ms.get(key))
+            if ms:
+                gbs = remote * 4096 / (ms * 1e-3) / 1e9
+                nv[name] = {"remote_rows_estimate": int(remote), "ms": ms, "achieved_gbs": gbs, "frac_of_770": gbs / 770.0}
+        roofline["nvlink"] = nv
 
     # ---- e2e: the public host-buffer API (unimoe_audio_b200.host.HostPipeline): every step copies its input
     # from pinned host memory and its whole 6-tuple back to pinned host memory inside the timed region; the
@@ -361,6 +387,7 @@ def run_ours(args):
             "gpu_launches": KERNELS_PER_STEP * args.steps if world == 1 else None,
             "roofline": roofline,
             "stage_ms": stage_ms,
+            "comm_stream_ms": comm_ms,
             "host_enqueue_ms_per_step": host_ms_per_step,
             "step_ms_first3": [a.elapsed_time(b) for a, b in step_ev[:3]],
             "step_ms_last3": [a.elapsed_time(b) for a, b in step_ev[-3:]],

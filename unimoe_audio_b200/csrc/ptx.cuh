@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 50000000u) {
+        if (++spins > 4000000u) {   // >> any legitimate wait (a tile is ~10 us); bounded so a protocol bug cannot hang the GPU
             printf("dcmoe: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
                    threadIdx.x, bar, parity);
             __trap();

@@ -131,6 +131,7 @@ class ExpertParallelDCMoE:
         self.comm_ctas = int(os.environ.get("DCMOE_EP_COMM_CTAS", "148"))   # grid cap of dispatch / partial combine (0 = full)
         self.gemm_ctas = int(os.environ.get("DCMOE_EP_GEMM_CTAS", "0"))   # CTAs of the shared GEMMs that run under comm (0 = all SMs)
         self._side = None
+        self.comm_events = []        # (name, start, end) CUDA events of the comm-stream kernels, filled when a stage hook is set
         self._local_cfg = None
         self._partial = None
 
@@ -305,9 +306,16 @@ class ExpertParallelDCMoE:
                 self._flag2 = torch.zeros(1, dtype=torch.int32, device=x.device)
             side, ev = self._side, self._ev
             ev[0].record(main)
+            timed = self.m.stage_hook is not None
             with torch.cuda.stream(side):
                 side.wait_event(ev[0])
+                if timed:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record(side)
                 self.phase_dispatch(self.comm_ctas)
+                if timed:
+                    t1.record(side)
+                    self.comm_events.append(("ep_dispatch", t0, t1))
                 dist.all_reduce(self._flag2, group=self.group)                   # barrier 1 (on the comm stream)
                 ev[1].record(side)
             self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas)             # overlaps the dispatch
@@ -320,7 +328,13 @@ class ExpertParallelDCMoE:
             ev[2].record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev[2])
+                if timed:
+                    t2, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t2.record(side)
                 self.phase_combine(None, 1, self.comm_ctas)                      # routed rows over NVLink -> fp32 partial
+                if timed:
+                    t3.record(side)
+                    self.comm_events.append(("ep_combine_gather", t2, t3))
                 ev[3].record(side)
             self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)             # overlaps the combine gather
             main.wait_event(ev[3])
