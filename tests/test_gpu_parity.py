@@ -485,3 +485,33 @@ def test_fused_decode_front_end_equals_three_kernel_path(T, masked, dev):
     routed = valid[t_pad:]
     assert torch.equal(ws_a.x_packed[: used - t_pad][routed], ws_b.x_packed[: used - t_pad][routed])
     assert torch.equal(ws_a.aux_loss, ws_b.aux_loss) or abs(ws_a.aux_loss.item() - ws_b.aux_loss.item()) <= 1e-6 * abs(ws_a.aux_loss.item())
+
+
+@pytest.mark.parametrize("dname", ["bf16", "fp32"])
+@pytest.mark.parametrize("T", [8, 700])
+def test_non_reference_dimensions_generic_kernels(dname, T, dev):
+    """A smaller layer (hidden 512, 4 routed + 1 null + 2 shared experts, I_d 256): exercises the run-time expert-count
+    paths of the router (templates <0, 0>), other tile counts in the GEMMs and the C oracle's general-n arithmetic."""
+    from unimoe_audio_b200 import DCMoE
+    dt = DT[dname]
+    cfg = dict(O.DEFAULT_CONFIG, hidden_size=512, mlp_dynamic_expert_num=4, mlp_dynamic_null_expert_num=1,
+               mlp_fixed_expert_num=2, dynamic_intermediate_size=256, shared_intermediate_size=128, mlp_dynamic_top_p=0.6)
+    W = O.make_weights(cfg, seed=9, dtype=dt)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    m = m.to(dt).to_empty(device=dev).eval()
+    m.load_state_dict({k: v.to(dev) for k, v in W.items()})
+    gen = torch.Generator().manual_seed(T)
+    x = torch.randn(1, T, 512, generator=gen).to(dt)
+    am = torch.rand(1, T, generator=gen) > 0.2
+    out = m(x.to(dev), am.to(dev), None)
+    torch.cuda.synchronize()
+    ref = O.forward(x, W, am, cfg=cfg, logits=out[1].cpu())
+    assert out[1].shape == (T, 7) and out[3].shape == (T, 7)
+    assert torch.equal(out[2].cpu(), ref.dynamic_top_k)
+    assert torch.equal(out[3].cpu(), ref.expert_mask)
+    assert torch.equal(out[4].cpu(), ref.global_weight)
+    np.testing.assert_allclose(out[5].item(), ref.aux_loss.item(), rtol=1e-5 if dname == "fp32" else 2e-3)
+    _check_layer(out[0].reshape(T, 512), ref.final_hidden_states.reshape(T, 512), dt)
+    lg_ref = torch.nn.functional.linear(x.reshape(-1, 512), W[O.GATE].to(dt)).float()
+    assert (out[1].float().cpu() - lg_ref).abs().max().item() <= (2e-2 if dname == "bf16" else 2e-5)

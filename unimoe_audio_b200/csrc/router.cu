@@ -308,13 +308,13 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
                 uint4 a[4], b[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {  // batch the HBM loads: 8 x 16 B in flight per lane
-                    a[u] = v0 ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;
-                    b[u] = v1 ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
+                    a[u] = (v0 && s0 + u < steps) ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;   // zero past this warp's K range
+                    b[u] = (v1 && s0 + u < steps) ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    uint4 q0 = wv0 ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
-                    uint4 q1 = wv1 ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
+                    uint4 q0 = (wv0 && s0 + u < steps) ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
+                    uint4 q1 = (wv1 && s0 + u < steps) ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
                     mma_bf16_16816(c0, a[u].x, b[u].x, a[u].y, b[u].y, q0.x, q0.y);
                     mma_bf16_16816(c0, a[u].z, b[u].z, a[u].w, b[u].w, q0.z, q0.w);
                     mma_bf16_16816(c1, a[u].x, b[u].x, a[u].y, b[u].y, q1.x, q1.y);
@@ -475,13 +475,13 @@ router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
                 uint4 a[4], b[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    a[u] = v0 ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;
-                    b[u] = v1 ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
+                    a[u] = (v0 && s0 + u < steps) ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;   // zero past this warp's K range
+                    b[u] = (v1 && s0 + u < steps) ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    uint4 q0 = wv0 ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
-                    uint4 q1 = wv1 ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
+                    uint4 q0 = (wv0 && s0 + u < steps) ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
+                    uint4 q1 = (wv1 && s0 + u < steps) ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
                     mma_bf16_16816(c0, a[u].x, b[u].x, a[u].y, b[u].y, q0.x, q0.y);
                     mma_bf16_16816(c0, a[u].z, b[u].z, a[u].w, b[u].w, q0.z, q0.w);
                     mma_bf16_16816(c1, a[u].x, b[u].x, a[u].y, b[u].y, q1.x, q1.y);
@@ -783,10 +783,10 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
                 uint4 a[4], b[4], q0[4], q1[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    a[u] = v0 ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;
-                    b[u] = v1 ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
-                    q0[u] = wv0 ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
-                    q1[u] = wv1 ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
+                    a[u] = (v0 && s0 + u < steps) ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;   // zero past this warp's K range
+                    b[u] = (v1 && s0 + u < steps) ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
+                    q0[u] = (wv0 && s0 + u < steps) ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
+                    q1[u] = (wv1 && s0 + u < steps) ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
