@@ -515,3 +515,49 @@ def test_non_reference_dimensions_generic_kernels(dname, T, dev):
     _check_layer(out[0].reshape(T, 512), ref.final_hidden_states.reshape(T, 512), dt)
     lg_ref = torch.nn.functional.linear(x.reshape(-1, 512), W[O.GATE].to(dt)).float()
     assert (out[1].float().cpu() - lg_ref).abs().max().item() <= (2e-2 if dname == "bf16" else 2e-5)
+
+
+@pytest.mark.parametrize("dims", [
+    dict(hidden_size=256, mlp_dynamic_expert_num=2, mlp_dynamic_null_expert_num=0, mlp_fixed_expert_num=1,
+         dynamic_intermediate_size=64, shared_intermediate_size=64, mlp_dynamic_top_p=0.7),
+    dict(hidden_size=768, mlp_dynamic_expert_num=6, mlp_dynamic_null_expert_num=2, mlp_fixed_expert_num=2,
+         dynamic_intermediate_size=192, shared_intermediate_size=96, mlp_dynamic_top_p=0.8),
+    dict(hidden_size=1024, mlp_dynamic_expert_num=12, mlp_dynamic_null_expert_num=2, mlp_fixed_expert_num=2,
+         dynamic_intermediate_size=384, shared_intermediate_size=192, mlp_dynamic_top_p=0.5),
+], ids=["h256-2+0+1", "h768-6+2+2", "h1024-12+2+2"])
+@pytest.mark.parametrize("T", [5, 300])
+def test_odd_configurations(dims, T, dev):
+    """Edge configurations of the constructor contract: no null expert, a single shared expert, 16 router columns,
+    intermediate sizes that end in a half tile -- bf16, single GPU and (when divisible) 2 virtual EP ranks."""
+    from unimoe_audio_b200 import DCMoE
+    from unimoe_audio_b200.ep import LocalRanks
+    dt = torch.bfloat16
+    cfg = dict(O.DEFAULT_CONFIG, **dims)
+    H = cfg["hidden_size"]
+    W = O.make_weights(cfg, seed=13, dtype=dt)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    m = m.to(dt).to_empty(device=dev).eval()
+    m.load_state_dict({k: v.to(dev) for k, v in W.items()})
+    gen = torch.Generator().manual_seed(T + H)
+    x = torch.randn(1, T, H, generator=gen).to(dt)
+    out = m(x.to(dev), None, None)
+    torch.cuda.synchronize()
+    ref = O.forward(x, W, None, cfg=cfg, logits=out[1].cpu())
+    assert torch.equal(out[2].cpu(), ref.dynamic_top_k) and torch.equal(out[3].cpu(), ref.expert_mask)
+    assert torch.equal(out[4].cpu(), ref.global_weight)
+    _check_layer(out[0].reshape(T, H), ref.final_hidden_states.reshape(T, H), dt)
+    lg_ref = torch.nn.functional.linear(x.reshape(-1, H), W[O.GATE].to(dt)).float()
+    assert (out[1].float().cpu() - lg_ref).abs().max().item() <= 2e-2
+    if T >= 16:
+        half = T // 2
+        xs = [x[:, :half].to(dev).contiguous(), x[:, half:].to(dev).contiguous()]
+        outs = LocalRanks(m, 2).forward(xs)
+        torch.cuda.synchronize()
+        got = torch.cat([o[0][0] for o in outs])
+        # the EP ranks run the large-T router on their half; logits may differ from the one-GPU call by a bf16 ulp
+        # (different K split), so compare against the oracle on the logits the ranks actually produced
+        lg = torch.cat([o[1] for o in outs]).cpu()
+        ref2 = O.forward(x, W, None, cfg=cfg, logits=lg)
+        assert torch.equal(torch.cat([o[3] for o in outs]).cpu(), ref2.expert_mask)
+        _check_layer(got, ref2.final_hidden_states.reshape(T, H), dt)
