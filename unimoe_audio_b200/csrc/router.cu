@@ -551,22 +551,28 @@ router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
 
 // ------------------------------------------------------------------------------------------------
 // TMA-fed persistent router (bf16, the production path).
-// One CTA per SM, 21 warps:
+// One CTA per SM, 29 warps:
 //   warp 0       TMA producer: the 16-token x block (16 x H bf16 = 64 KB) is fetched as 64-column boxes
 //                (cp.async.bulk.tensor.2d, 128B swizzle) into a 2-stage smem ring -- up to 128 KB in flight per SM
 //                with no register cost, which is what it takes to stream HBM at full rate from ~7 blocks per SM;
 //   warps 1-4    gate MMA: ldmatrix.x4 (swizzled) + mma.sync.m16n8k16 against W_g held in smem in fragment order,
 //                K split four ways, partial logits into a 4-stage smem ring;
-//   warps 5-20   routing: two groups of 8 warps (one 16-token block per group per round, half-warp per token)
+//   warps 5-28   routing: three groups of 8 warps (one 16-token block per group per round, half-warp per token)
 //                running the shuffle/exp chains of route_token<> while the next blocks stream in.
 // mbarriers pace the x ring; named barriers (bar.arrive / bar.sync) pace the logits ring.
-constexpr int kTmaThreads = 21 * 32;
+constexpr int kTmaThreads = 29 * 32;
+constexpr int kRouteGroups = 3;
 constexpr int kXStageBytes = kRouterBlock * 2048 * 2;   // sized for H = 2048 (checked at launch: H <= 2048)
 constexpr int kXStages = 2;
-constexpr int kWfBytes = (2048 / 16) * 2 * 32 * 8;      // W_g fragments: [k16][n-tile][lane] x 8 B
-constexpr int kRedStages = 4;
-constexpr int kRouterSmem = kXStages * kXStageBytes + kWfBytes + kRedStages * 4 * kRouterBlock * 16 * 4 +
-                            2 * 2 * kRouterBlock * kMaxDyn * 4 + 64 + 1024;
+constexpr int kRedStages = 6;                           // stage s is always consumed by routing group s % 3
+static_assert((kXStages & (kXStages - 1)) == 0, "x ring is indexed with a mask");
+static_assert(kRedStages % kRouteGroups == 0 && 2 * kRedStages + kRouteGroups <= 15, "named barrier ids 1..15");
+// W_g fragments in smem: n-tile 0 (experts 0-7) [k16][32 lanes] x 8 B, n-tile 1 (experts 8..E-1) [k16][4 (E-8) lanes] x 8 B
+__host__ __device__ constexpr int router_wf_bytes(int H, int E) { return (H / 16) * (32 + 4 * (E > 8 ? E - 8 : 0)) * 8; }
+__host__ __device__ constexpr int router_smem_bytes(int H, int E) {
+    return kXStages * kXStageBytes + router_wf_bytes(H, E) + kRedStages * 4 * kRouterBlock * 16 * 4 +
+           kRouteGroups * 2 * 2 * kRouterBlock * kMaxDyn * 4 + 64 + 1024;
+}
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -585,11 +591,14 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t xs = base;                                                 // [kXStages][H/64][16 rows][128 B]
-    uint2* wf = reinterpret_cast<uint2*>(gbase + kXStages * kXStageBytes);    // [H/16][2][32]
-    float* red = reinterpret_cast<float*>(gbase + kXStages * kXStageBytes + kWfBytes);   // [4][4][16][16]
-    int* s_cnt = reinterpret_cast<int*>(red + kRedStages * 4 * kRouterBlock * 16);       // [2 groups][16][16]
-    float* s_prob = reinterpret_cast<float*>(s_cnt + 2 * kRouterBlock * kMaxDyn);
-    const uint32_t bars = smem_u32(s_prob + 2 * kRouterBlock * kMaxDyn);
+    const int E_ = NE ? NE : rc.E;
+    const int L1 = (E_ > 8 ? E_ - 8 : 0) * 4;                                 // lanes of n-tile 1 that hold real experts
+    uint2* wf0 = reinterpret_cast<uint2*>(gbase + kXStages * kXStageBytes);   // [H/16][32]
+    uint2* wf1 = wf0 + (H >> 4) * 32;                                         // [H/16][L1]
+    float* red = reinterpret_cast<float*>(gbase + kXStages * kXStageBytes + router_wf_bytes(H, E_));   // [6][4][16][16]
+    int* s_cnt = reinterpret_cast<int*>(red + kRedStages * 4 * kRouterBlock * 16);       // [3 groups][2 buffers][16][16]
+    float* s_prob = reinterpret_cast<float*>(s_cnt + kRouteGroups * 2 * kRouterBlock * kMaxDyn);
+    const uint32_t bars = smem_u32(s_prob + kRouteGroups * 2 * kRouterBlock * kMaxDyn);
     auto x_full = [&](int s) { return bars + 8u * s; };
     auto x_empty = [&](int s) { return bars + 8u * (kXStages + s); };
 
@@ -605,32 +614,45 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         }
         fence_barrier_init();
     }
-    __syncthreads();   // barriers initialised; the producer starts streaming x right away
-    if (warp != 0) {
+    __syncthreads();   // barriers initialised
+    int prod_it = 0;
+    if (warp == 0) {
+        // the producer puts the first stages in flight before anyone stages W_g
+        for (int blk = blockIdx.x; blk < n_blocks && prod_it < kXStages; blk += gridDim.x, ++prod_it) {
+            if (lane == 0) {
+                mbar_expect_tx(x_full(prod_it), (uint32_t)(kRouterBlock * H * 2));
+                for (int c = 0; c < n_chunks; ++c)
+                    tma_load_2d(xs + prod_it * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
+                                x_full(prod_it));
+            }
+            __syncwarp();
+        }
+    } else {
         // W_g -> smem in mma B-fragment order (done by the 20 non-producer warps while the first x blocks are in
         // flight): wf[k16][nt][lane] = {W[n][16 k16 + 2 tq .. +1], W[n][16 k16 + 8 + 2 tq .. +1]}, n = 8 nt + lane / 4,
         // tq = lane % 4; rows n >= E are zero.  One 16-byte load (8 consecutive k of one row) feeds four entries.
-        uint32_t* wf32 = reinterpret_cast<uint32_t*>(wf);
         const int n_kc = H >> 3;                       // 16-byte chunks per row
         for (int i = tid - 32; i < 16 * n_kc; i += kTmaThreads - 32) {
             const int n = i / n_kc, kc = i - n * n_kc;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (n < E) v = ld_ca_v4(wg + (int64_t)n * H + kc * 8);
-            const int k16 = kc >> 1, hi = kc & 1, nt = n >> 3, g = n & 7;
-            uint32_t* dst = wf32 + (((k16 * 2 + nt) * 32 + g * 4) << 1) + hi;
+            if (n >= E) continue;
+            const int k16 = kc >> 1, hi = kc & 1, g = n & 7;
+            uint32_t* dst = n < 8 ? reinterpret_cast<uint32_t*>(wf0) + ((k16 * 32 + g * 4) << 1) + hi
+                                  : reinterpret_cast<uint32_t*>(wf1) + ((k16 * L1 + g * 4) << 1) + hi;
             dst[0] = v.x;
             dst[2] = v.y;
             dst[4] = v.z;
             dst[6] = v.w;
         }
-        named_bar_sync(13, kTmaThreads - 32);
     }
 
+    __syncthreads();   // W_g fragments staged
     constexpr int kFullCount = 128 + 256;   // gate warps + one routing group
     if (warp == 0) {
-        // ================= TMA producer =================
-        int it = 0;
-        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        // ================= TMA producer (continues after the stages issued above) =================
+        int it = prod_it;
+        for (int blk = blockIdx.x + prod_it * gridDim.x; blk < n_blocks; blk += gridDim.x, ++it) {
             const int st = it & (kXStages - 1);
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
             mbar_wait(x_empty(st), ph ^ 1u);
@@ -653,7 +675,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
             const int st = it & (kXStages - 1);
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
-            const int rs = it & (kRedStages - 1);
+            const int rs = it % kRedStages;
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
             mbar_wait(x_full(st), ph);
             for (int cc = 0; cc < chunks_per_warp; ++cc) {
@@ -665,15 +687,15 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                     uint32_t a0, a1, a2, a3;
                     ldmatrix_x4(tile + lrow * 128 + ((lchunk ^ (lrow & 7)) << 4), a0, a1, a2, a3);
                     const int k16 = c * 4 + s4;
-                    const uint2 b0 = wf[(k16 * 2 + 0) * 32 + lane];
-                    const uint2 b1 = wf[(k16 * 2 + 1) * 32 + lane];
+                    const uint2 b0 = wf0[k16 * 32 + lane];
+                    const uint2 b1 = lane < L1 ? wf1[k16 * L1 + lane] : make_uint2(0u, 0u);
                     mma_bf16_16816(c0, a0, a1, a2, a3, b0.x, b0.y);
                     mma_bf16_16816(c1, a0, a1, a2, a3, b1.x, b1.y);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(x_empty(st));           // this warp is done reading the x stage
-            if (it >= kRedStages) named_bar_sync(5 + rs, kFullCount);
+            if (it >= kRedStages) named_bar_sync(7 + rs, kFullCount);
             float* r = red + ((rs * 4 + wq) * kRouterBlock) * 16;
             r[g * 16 + 2 * tq] = c0[0];
             r[g * 16 + 2 * tq + 1] = c0[1];
@@ -686,15 +708,15 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             named_bar_arrive(1 + rs, kFullCount);
         }
     } else {
-        // ================= routing warps: group 0 = warps 5-12, group 1 = warps 13-20 =================
+        // ================= routing warps: group g = warps 5+8g .. 12+8g =================
         const int grp = (warp - 5) >> 3, rw_ = (warp - 5) & 7;
         const int half = lane >> 4, j = lane & 15;
         const int gtid = tid - (5 + grp * 8) * 32;
-        int* cnt = s_cnt + grp * kRouterBlock * kMaxDyn;
-        float* prob = s_prob + grp * kRouterBlock * kMaxDyn;
+        int* cnt0 = s_cnt + grp * 2 * kRouterBlock * kMaxDyn;
+        float* prob0 = s_prob + grp * 2 * kRouterBlock * kMaxDyn;
         int it = grp;
-        for (int blk = blockIdx.x + grp * gridDim.x; blk < n_blocks; blk += 2 * gridDim.x, it += 2) {
-            const int rs = it & (kRedStages - 1);
+        for (int blk = blockIdx.x + grp * gridDim.x; blk < n_blocks; blk += kRouteGroups * gridDim.x, it += kRouteGroups) {
+            const int rs = it % kRedStages;
             const int64_t tok0 = (int64_t)blk * kRouterBlock;
             const int tl = rw_ * 2 + half;
             const int64_t t = tok0 + tl;
@@ -706,7 +728,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                 l = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[kRouterBlock * 16]), r[2 * kRouterBlock * 16]), r[3 * kRouterBlock * 16]);
                 l = bf16_round(l);
             }
-            if ((int64_t)blk + (int64_t)kRedStages * gridDim.x < n_blocks) named_bar_arrive(5 + rs, kFullCount);
+            if ((int64_t)blk + (int64_t)kRedStages * gridDim.x < n_blocks) named_bar_arrive(7 + rs, kFullCount);
             const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
             int raw, mk;
             float gw, ga;
@@ -717,9 +739,12 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                 expert_mask[t * E + j] = mk;
                 if (j == 0) top_k[t] = raw;
             }
+            const int sbuf = (it / kRouteGroups) & 1;                 // double-buffered block statistics
+            int* cnt = cnt0 + sbuf * kRouterBlock * kMaxDyn;
+            float* prob = prob0 + sbuf * kRouterBlock * kMaxDyn;
             cnt[tl * kMaxDyn + j] = (valid && j < n_dyn) ? mk : 0;
             prob[tl * kMaxDyn + j] = (valid && j < n_dyn) ? ga : 0.0f;
-            named_bar_sync(9 + grp, 256);
+            named_bar_sync(13 + grp, 256);
             if (gtid < n_dyn) {
                 int c = 0;
                 float pr = 0.0f;
@@ -731,7 +756,6 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                 block_counts[(int64_t)blk * n_dyn + gtid] = c;
                 block_probs[(int64_t)blk * n_dyn + gtid] = pr;
             }
-            named_bar_sync(11 + grp, 256);   // stats buffer may be rewritten
         }
     }
 }
@@ -983,12 +1007,15 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // (decode-sized calls were measured with the one-CTA-per-block kernel too: 21.8 us vs 14.7 us for the TMA-fed
     // kernel at T = 2, so the persistent kernel is used at every size)
-    if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0) {
+    const int router_smem = router_smem_bytes(cfg->hidden_size, rc.E);
+    if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
+        router_smem <= 232448) {
         static bool attr_done = false;
         if (!attr_done) {
-            int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouterSmem), "cudaFuncSetAttribute(router_tma<9,11>)");
+            const int max_smem = router_smem_bytes(2048, 16) > 232448 ? 232448 : router_smem_bytes(2048, 16);
+            int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<9,11>)");
             if (rc2) return rc2;
-            rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRouterSmem), "cudaFuncSetAttribute(router_tma<0,0>)");
+            rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<0,0>)");
             if (rc2) return rc2;
             attr_done = true;
         }
@@ -997,11 +1024,11 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         if (rc2) return rc2;
         dim3 g2((unsigned)(n_blocks < sms ? n_blocks : sms)), b2(kTmaThreads);
         if (ref_shape)
-            router_tma_kernel<9, 11><<<g2, b2, kRouterSmem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+            router_tma_kernel<9, 11><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
                 (__nv_bfloat16*)global_weight, block_counts, block_probs);
         else
-            router_tma_kernel<0, 0><<<g2, b2, kRouterSmem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+            router_tma_kernel<0, 0><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
                 (__nv_bfloat16*)global_weight, block_counts, block_probs);
         return check_cuda(cudaGetLastError(), "router_tma_kernel launch");
