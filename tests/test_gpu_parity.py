@@ -349,6 +349,32 @@ def test_cta_pair_ffn_matches_single_cta_ffn(B, S, dev):
     _check_layer(out2[0].reshape(B * S, 2048), ref.final_hidden_states.reshape(B * S, 2048), dt)
 
 
+@pytest.mark.parametrize("T,masked", [(1, False), (2, False), (16, False), (17, True), (32, False), (33, False), (64, True)])
+def test_decode_sized_weight_streaming_ffn_matches_large_tiles(T, masked, dev):
+    """T <= 64 runs the weight-streaming tcgen05 GEMMs (ffn_tcgen05_stream.cu: 16-column granules divided evenly over
+    the SMs, 16/32/64-row A box, register-direct stores).  Same K order and fp32 accumulation as the 128x256 tiles,
+    so the layer output must equal the CTA-pair kernel's (which always uses the large tiles) bit for bit, and match
+    the oracle."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=4)
+    g = torch.Generator().manual_seed(500 + T)
+    x = torch.randn(T, 1, 2048, generator=g).to(dt).to(dev)
+    mask = None
+    if masked:
+        mask = (torch.rand(T, 1, generator=g) > 0.3).to(torch.int64).to(dev)
+    m.ffn_impl = 0
+    out_small = [t.clone() for t in m(x, mask, None)]
+    m.ffn_impl = 2
+    out_large = m(x, mask, None)
+    torch.cuda.synchronize()
+    m.ffn_impl = None
+    assert torch.equal(out_small[3], out_large[3])
+    assert torch.equal(out_small[0], out_large[0])
+    ref = O.forward(x.cpu(), W, None if mask is None else mask.cpu(), logits=out_small[1].cpu())
+    assert torch.equal(out_small[3].cpu(), ref.expert_mask)
+    _check_layer(out_small[0].reshape(T, 2048), ref.final_hidden_states.reshape(T, 2048), dt)
+
+
 def test_stack_of_layers_chained_config3_shape(dev):
     """BASELINE.json config 3 in miniature: several DCMoE layers with independent weights, activations chained
     (RMS-normalised between layers as the decoder does before the MoE, model.py:239-241), one shared workspace.
