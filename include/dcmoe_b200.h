@@ -169,14 +169,16 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *   y            [row_capacity, H] D      already weighted expert outputs
  *   impl         0 = tcgen05/TMEM/TMA grouped GEMM, one CTA per tile (bf16 only); 2 = the same on CTA pairs
  *                (tcgen05.mma.cta_group::2, 256-row tiles); 1 = CUDA-core fp32-accumulate GEMM (the fp32 layer
- *                path; also usable with bf16 for cross-checking); 3 = experimental decode kernels (T <= 64, bf16:
- *                weights streamed once as the M operand of mma.sync; measured no faster than impl 0, never auto-selected)
+ *                path; also usable with bf16 for cross-checking); 3 = weight-streaming tcgen05 GEMMs for decode-sized
+ *                calls (bf16, T <= 64: weights as the MMA M operand, one K pass per SM; h and y bit-equal to impl 0's
+ *                128 x 256 tiles).  impl 0 selects them by itself when T <= 64 (see bit 20; DCMOE_FFN_STREAM=0 disables)
  *   phase        low 4 bits: 0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
  *                put CUDA events between the two launches.  Bits 4-5 select the tile group (tcgen05 only):
  *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism
  *                runs the shared experts while the dispatch is still in flight.  Bits 8-19: cap on the number of
  *                persistent CTAs (0 = one per SM), to leave SMs to concurrently running dispatch / combine kernels.
- *                Bit 20: never select the decode kernels automatically (set by expert parallelism)
+ *                Bit 20: never select the decode-sized kernels automatically (set by expert parallelism, where a
+ *                rank can own more rows than it has tokens)
  */
 int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                       int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,

@@ -451,21 +451,33 @@ def test_fused_residual_add(dev):
     assert torch.equal(fused[3], plain[3])
 
 
-@pytest.mark.parametrize("B,S", [(2, 1), (1, 8), (3, 11)])
-def test_experimental_decode_ffn_kernels(B, S, dev):
-    """impl = 3 (weights as the mma.sync M operand, T <= 64) against the default tcgen05 path."""
+@pytest.mark.parametrize("max_ctas", [0, 100, 37])
+def test_weight_streaming_ffn_on_a_capped_grid(max_ctas, dev):
+    """dcmoe_grouped_ffn impl = 3 (weight-streaming tcgen05 GEMMs) called through the C ABI with a grid cap: the
+    granule split changes with the CTA count, h and y must not (bit-equal to the large-tile kernel); a cap too
+    small for the widest segment is refused."""
+    from unimoe_audio_b200 import ops
     dt = torch.bfloat16
     m, W = _module(dt, dev, seed=2)
-    x = torch.randn(B, S, 2048, generator=torch.Generator().manual_seed(5 + S)).to(dt).to(dev)
-    m.ffn_impl = 0
-    ref = [t.clone() for t in m(x, None, None)]
-    m.ffn_impl = 3
-    out = m(x, None, None)
+    x = torch.randn(9, 1, 2048, generator=torch.Generator().manual_seed(77)).to(dt).to(dev)
+    m.ffn_impl = 2
+    m(x, None, None)
+    torch.cuda.synchronize()
+    ws = m.last_workspace
+    h_ref, y_ref = ws.h.clone(), ws.y.clone()
+    ws.h.zero_(); ws.y.zero_()
+    phase_bits = max_ctas << 8
+    if max_ctas == 37:      # 37 CTAs / 9 groups = 4 per group -> 172 / 4 = 43 granules > 16: refused
+        with pytest.raises(RuntimeError):
+            ops.grouped_ffn(x.reshape(9, 2048), m._w13, m._w2, ws, 3, phase=phase_bits)
+        return
+    ops.grouped_ffn(x.reshape(9, 2048), m._w13, m._w2, ws, 3, phase=phase_bits)
     torch.cuda.synchronize()
     m.ffn_impl = None
-    a, b = out[0].float(), ref[0].float()
-    assert (a - b).abs().max().item() <= 1e-2 * b.abs().max().item()
-    assert ((a - b).norm() / b.norm()).item() < 3e-3
+    mt = ws.mtiles[: int(ws.n_mtiles.item())].cpu()
+    for a_row, out_row, group, n in mt.tolist():
+        assert torch.equal(ws.h[out_row:out_row + n], h_ref[out_row:out_row + n])
+        assert torch.equal(ws.y[out_row:out_row + n], y_ref[out_row:out_row + n])
 
 
 @pytest.mark.parametrize("T,masked", [(1, False), (2, False), (17, True), (64, False), (33, True)])

@@ -150,8 +150,6 @@ int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const
 bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int);
 int launch_ffn_tcgen05_stream(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                               const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
-int launch_ffn_decode(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
-                      const dcmoe_sizes&, PlanView, void*, void*, int, cudaStream_t);
 int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                             const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 
@@ -282,20 +280,15 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, const_cast<void*>(plan), &sz, &pv))) return rc;
     // decode-sized calls (T <= 64): weight-streaming tcgen05 GEMMs (ffn_tcgen05_stream.cu; bit-identical h and y).
-    // impl 4 asks for them explicitly; impl 0 picks them unless the caller vetoes (bit 20), selects tile groups, or
+    // impl 3 asks for them explicitly; impl 0 picks them unless the caller vetoes (bit 20), selects tile groups, or
     // DCMOE_FFN_STREAM=0 (A/B measurements)
-    if (impl == 4) return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
+    if (impl == 3) return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
                                                     phase, max_ctas, (cudaStream_t)stream);
     if (impl == 0 && !no_decode && group_sel == 0 && ffn_stream_applicable(T, cfg, sz, max_ctas)) {
         const char* e = getenv("DCMOE_FFN_STREAM");
         if (!(e && e[0] == '0'))
             return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase,
                                              max_ctas, (cudaStream_t)stream);
-    }
-    if (impl == 3) {
-        // experimental decode kernels (weights as the mma.sync M operand).  Measured equal to the tcgen05 path at
-        // T = 2 (65 us for both GEMMs) and slower from T = 16 up, so they are never selected automatically.
-        return launch_ffn_decode(x, x_packed, w13, w2, row_scale, T, cfg, sz, pv, h, y, phase, (cudaStream_t)stream);
     }
     if (impl == 2) {
         if (cfg->dtype != DCMOE_BF16) { set_error("tcgen05 FFN is bf16 only"); return DCMOE_ERR_INVALID; }

@@ -302,8 +302,8 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     const int64_t packed_rows = row_capacity - sz.t_pad;
     if ((rc = make_tensor_map_bf16(&m_x, x, T, H, BM))) return rc;
     if ((rc = make_tensor_map_bf16(&m_xp, x_packed, packed_rows > 0 ? packed_rows : 1, H, BM))) return rc;
-    const int bn = BN;   // (128-column tiles were measured for decode sizes: slower -- the 128-row A tile then is
-                         // half of every stage's bytes; decode sizes use ffn_decode.cu instead)
+    const int bn = BN;   // (decode sizes, T <= 64, run ffn_tcgen05_stream.cu instead: narrower tiles of this kernel
+                         // were measured slower -- whole tiles per SM leave the chip 52-68 % busy)
     if ((rc = make_tensor_map_bf16(&m_w13, w13, (int64_t)G * 2 * Id, H, bn))) return rc;
     if ((rc = make_tensor_map_bf16(&m_h_st, h, row_capacity, Id, 32))) return rc;
     if ((rc = make_tensor_map_bf16(&m_h_ld, h, row_capacity, Id, BM))) return rc;

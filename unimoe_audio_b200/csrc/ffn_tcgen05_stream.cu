@@ -3,21 +3,24 @@
 // The generation loop calls the layer with T = 2N tokens (reference model.py:1149-1203).  Every m-tile then holds
 // a handful of rows and the layer is bound by reading each hit expert's weights ONCE (up to 304 MB per layer).  The
 // 128 x 256 tiles of ffn_tcgen05.cu fit that badly: 22 + 8 n-tiles per group leave the 148 SMs 52-68 % busy (whole
-// tiles per SM), and a 128-row A box is a third of every stage.  tools/probe_stream.cu measured what the TMA path
-// needs to stream HBM at full rate (6.7-7.0 TB/s): >= 16 KB per ring stage, and small boxes issued by many lanes
-// at once rather than one box per stage from one lane (1.8-3.4 TB/s).  So here:
-//   * the output columns of ALL m-tiles are cut into 16-column granules (GEMM-1: 16 h columns = 16 gate + 16 up
+// tiles per SM).  What was measured on the way here (tools/probe_stream.cu, DCMOE_FFN_STREAM_DEBUG=1 counters):
+//   * TMA streams HBM at 6.7-7.0 TB/s with >= 16 KB per ring stage; issuing a box costs the producer ~50 cycles
+//     whatever its size, and a ring stage ~200 cycles of mbarrier handshake, so at this size the STAGE COUNT per SM
+//     is the cost to balance, and boxes must be as large as the rows allow;
+//   * tcgen05.mma instructions that accumulate into the same TMEM tile are a ~140-cycle dependent chain each.
+// So here:
+//   * the output columns of every m-tile are cut into 16-column granules (GEMM-1: 16 h columns = 16 gate + 16 up
 //     rows of W13; GEMM-2: 16 y columns); the CTAs are dealt evenly to the hit weight groups and each group's
-//     granules evenly to its CTAs, so every SM makes ONE pass over K and streams the same weight bytes (+-1
+//     granules evenly to its CTAs: every SM makes exactly ONE pass over K and streams the same weight bytes (+-1
 //     granule) whatever the number of hit experts;
-//   * a CTA's segment is up to 16 granules: one or two accumulators of N = 16..256 columns (all 512 TMEM columns,
-//     no double buffering -- there is one tile per CTA), B = one 16-row TMA box per granule half, each issued by
-//     its own producer lane;
-//   * the A box is 16 / 32 / 64 rows (the MMA still reads 128 rows: the rows past the box are whatever follows in
-//     shared memory and only reach accumulator rows that are never stored);
-//   * the epilogue stores the valid rows straight from registers (SwiGLU + routing weight fused, as in the large
-//     kernel).
-// Same K order and fp32 accumulation per output element as ffn_tcgen05.cu, hence bit-identical h and y.
+//   * the WEIGHTS are the MMA's M operand (128 rows = 8 granules per M-tile) and the <= 64 token rows its N operand:
+//     no tensor-core work or shared-memory read is padding; an M-tile that is only partly loaded computes lanes
+//     that nobody reads.  Up to 16 granules per CTA = 2 (GEMM-2) / 4 (GEMM-1: gate and up) accumulators;
+//   * runs of consecutive weight rows are fetched with the largest TMA boxes that tile them (16/32/64/128 rows),
+//     one box per producer lane; the token box is 16 / 32 / 64 rows;
+//   * the epilogue reads TMEM lane = output column, TMEM column = token, applies SwiGLU and the routing weight
+//     (GEMM-1) and stores the valid tokens straight from registers.
+// Same K order and fp32 accumulation per output element as ffn_tcgen05.cu: h and y are bit-identical (tested).
 #include <cuda.h>
 
 #include <algorithm>
@@ -39,7 +42,6 @@ constexpr int SLACK_BYTES = BM * BK * 2;      // the MMA reads a full 128-row A 
 constexpr int BAR_BYTES = 512;                // full[16] empty[16] tfull[2] tempty[2] tmem slot
 constexpr int SMEM_BYTES = RING_BYTES + SLACK_BYTES + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COLS = 256;
 constexpr int NUM_THREADS = 256;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {   // K-major, SWIZZLE_128B, SBO 1024 B
@@ -77,7 +79,8 @@ struct StreamParams {
     const dcmoe_mtile* mtiles;
     const int32_t* n_mtiles;
     const float* row_scale;
-    int a_alloc;        // bytes of the A box (box rows x 128)
+    int a_alloc;        // bytes of the token box (n_tok rows x 128)
+    int n_tok;          // token rows per box = MMA N: 16 / 32 / 64
     int stage_bytes;    // a_alloc + widest segment's B boxes
     int stages;
     __nv_bfloat16* out; // h / y
@@ -156,9 +159,13 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
 
     const long long t_start = p.dbg ? clock64() : 0;
     const Segment sg = cta_segment(*p.n_mtiles, p.gpg);
-    // accumulators: sub-segment 0 = the first ng0 granules (TMEM columns [0, 256)), sub-segment 1 = the rest
-    // (columns [256, 512)); GEMM-1 holds gate and up columns of a granule, so 8 granules fill one accumulator
-    constexpr int kSub = SWIGLU ? ACC_COLS / (2 * GR) : ACC_COLS / GR;
+    // The WEIGHTS are the MMA's M operand (128 rows = 8 granules per M-tile) and the token rows its N operand
+    // (N = the A box: 16 / 32 / 64 tokens): D[weight row, token].  Nothing of the tensor-core work or of its shared
+    // memory reads is padding, and an M-tile that is only partly loaded just computes lanes nobody reads.
+    // Sub-segment 0 = the first 8 granules, sub-segment 1 = the rest; GEMM-1 keeps gate and up rows of a
+    // sub-segment in two M-tiles, so that TMEM lane i holds gate and up of the SAME h column (in different columns).
+    // TMEM columns: accumulator a = 2 * sub + half (GEMM-1) / sub (GEMM-2) at [a * n_tok, (a + 1) * n_tok).
+    constexpr int kSub = BM / GR;   // 8 granules = 128 weight rows = one MMA M-tile
     const int ng0 = min(sg.ng, kSub), ng1 = sg.ng - ng0;
     const int nb0 = SWIGLU ? 2 * ng0 : ng0, nb1 = SWIGLU ? 2 * ng1 : ng1;
     const int nb = nb0 + nb1;                         // B boxes per stage (<= 32, one per producer lane)
@@ -245,7 +252,7 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
         }
     } else if (sg.ng > 0 && warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc0 = make_idesc(nb0 * GR), idesc1 = make_idesc(nb1 * GR);
+        const uint32_t idesc = make_idesc(p.n_tok);
         int stage = 0;
         uint32_t phase = 0;
         long long d_wait = 0, d_issue = 0;
@@ -255,16 +262,25 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
             tc_fence_after();
             const long long t1 = p.dbg ? clock64() : 0;
             if (lane == 0) {
-                const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-                const uint64_t adesc = make_smem_desc(a_addr);
-                const uint64_t bdesc0 = make_smem_desc(a_addr + p.a_alloc);
-                const uint64_t bdesc1 = make_smem_desc(a_addr + p.a_alloc + nb0 * BOX_BYTES);
+                const uint32_t tok_addr = smem_base + stage * p.stage_bytes;
+                const uint64_t tdesc = make_smem_desc(tok_addr);
+                const uint32_t w_addr = tok_addr + p.a_alloc;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc0 + (uint64_t)(2 * k), idesc0, (uint32_t)((kb | k) != 0));
-                    if (nb1 > 0)
-                        umma_bf16(tmem_base + ACC_COLS, adesc + (uint64_t)(2 * k), bdesc1 + (uint64_t)(2 * k), idesc1,
-                                  (uint32_t)((kb | k) != 0));
+                    const uint32_t accum = (uint32_t)((kb | k) != 0);
+                    // M-tiles in B-tile order: [sub 0: gate | up] [sub 1: gate | up]  (GEMM-2: [sub 0] [sub 1])
+                    umma_bf16(tmem_base, make_smem_desc(w_addr) + (uint64_t)(2 * k), tdesc + (uint64_t)(2 * k), idesc, accum);
+                    if (SWIGLU)
+                        umma_bf16(tmem_base + p.n_tok, make_smem_desc(w_addr + ng0 * BOX_BYTES) + (uint64_t)(2 * k),
+                                  tdesc + (uint64_t)(2 * k), idesc, accum);
+                    if (ng1 > 0) {
+                        const uint32_t w1 = w_addr + nb0 * BOX_BYTES;
+                        umma_bf16(tmem_base + (SWIGLU ? 2 : 1) * p.n_tok, make_smem_desc(w1) + (uint64_t)(2 * k),
+                                  tdesc + (uint64_t)(2 * k), idesc, accum);
+                        if (SWIGLU)
+                            umma_bf16(tmem_base + 3 * p.n_tok, make_smem_desc(w1 + ng1 * BOX_BYTES) + (uint64_t)(2 * k),
+                                      tdesc + (uint64_t)(2 * k), idesc, accum);
+                    }
                 }
                 umma_commit(empty_bar(stage));
                 if (kb == p.num_kb - 1) umma_commit(tfull_bar);
@@ -282,51 +298,34 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
             p.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;   // last MMA issued
         }
     } else if (sg.ng > 0 && warp >= 4) {
-        // ================= epilogue: valid rows straight from TMEM to h / y =================
+        // ================= epilogue: TMEM lane = output column, TMEM column = token =================
         const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
         const dcmoe_mtile mt = p.mtiles[sg.m];
-        const int rows_here = mt.rows - wq * 32;
-        if (rows_here > 0) {
-            const int64_t r = (int64_t)mt.out_row + wq * 32 + lane;
-            float sa = 1.0f, sb = 1.0f;
-            if (SWIGLU && lane < rows_here) {
-                sa = p.row_scale[2 * r];
-                sb = p.row_scale[2 * r + 1];
-            }
-            const bool shared_grp = mt.group == p.n_real;
-            mbar_wait(tfull_bar, 0u);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(wq * 32) << 16);
-            for (int i = 0; i < sg.ng; ++i) {
-                uint32_t packed[8];
-                const int col0 = (sg.g0 + i) * GR;
-                const int sub = i >= ng0;
-                const int li = sub ? i - ng0 : i, ngs = sub ? ng1 : ng0;
-                const uint32_t t_sub = t_row + (uint32_t)(sub * ACC_COLS);
-                if (SWIGLU) {
-                    uint32_t g[16], u[16];
-                    tmem_ld16(t_sub + (uint32_t)(GR * li), g);
-                    tmem_ld16(t_sub + (uint32_t)(GR * (ngs + li)), u);
-                    tmem_ld_wait();
-                    const float sc = (shared_grp && col0 >= p.split_col) ? sb : sa;
+        const bool shared_grp = mt.group == p.n_real;
+        mbar_wait(tfull_bar, 0u);
+        tc_fence_after();
+        for (int sub = 0; sub < 2; ++sub) {
+            const int ngs = sub ? ng1 : ng0;
+            const int c_local = wq * 32 + lane;                       // column inside the sub-segment
+            if (wq * 32 >= ngs * GR) continue;                        // (warp-uniform) no valid lane in this quarter
+            const bool lane_ok = c_local < ngs * GR;
+            const int col = (sg.g0 + sub * ng0) * GR + c_local;        // h / y column of this lane
+            const uint32_t t_acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((SWIGLU ? 2 : 1) * sub * p.n_tok);
+            const int sel = (SWIGLU && shared_grp && col >= p.split_col) ? 1 : 0;
+            for (int n0 = 0; n0 < mt.rows; n0 += 16) {                // 16 tokens per TMEM load
+                uint32_t g[16], u[16];
+                tmem_ld16(t_acc + (uint32_t)n0, g);
+                if (SWIGLU) tmem_ld16(t_acc + (uint32_t)(p.n_tok + n0), u);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float v0 = silu_mul(__uint_as_float(g[2 * e]), __uint_as_float(u[2 * e])) * sc;
-                        const float v1 = silu_mul(__uint_as_float(g[2 * e + 1]), __uint_as_float(u[2 * e + 1])) * sc;
-                        packed[e] = pack_bf16(v0, v1);
+                for (int e = 0; e < 16; ++e) {
+                    const int n = n0 + e;
+                    if (n < mt.rows && lane_ok) {
+                        const int64_t r = (int64_t)mt.out_row + n;
+                        float v = __uint_as_float(g[e]);
+                        if (SWIGLU) v = silu_mul(v, __uint_as_float(u[e])) * p.row_scale[2 * r + sel];
+                        p.out[r * p.ld_out + col] = __float2bfloat16_rn(v);
                     }
-                } else {
-                    uint32_t v[16];
-                    tmem_ld16(t_sub + (uint32_t)(GR * li), v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        packed[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                }
-                if (lane < rows_here) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.ld_out + col0);
-                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                 }
             }
         }
@@ -364,7 +363,7 @@ bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes
     const int G = cfg->n_real + 1;
     if (n_ctas < G) return false;
     const int per_group = n_ctas / G;
-    return ceil_div(cfg->dynamic_intermediate_size / GR, per_group) <= 16 && ceil_div(cfg->hidden_size / GR, per_group) <= 32;
+    return ceil_div(cfg->dynamic_intermediate_size / GR, per_group) <= 16 && ceil_div(cfg->hidden_size / GR, per_group) <= 16;
 }
 
 int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
@@ -413,6 +412,7 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     p1.n_mtiles = pv.n_mtiles;
     p1.row_scale = row_scale;
     p1.a_alloc = a_box * BK * 2;
+    p1.n_tok = a_box;
     p1.stage_bytes = p1.a_alloc + 2 * p1.max_gran * BOX_BYTES;
     p1.stages = std::min(MAX_STAGES, RING_BYTES / p1.stage_bytes);
     p1.out = static_cast<__nv_bfloat16*>(h);
