@@ -185,6 +185,17 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
                       int impl, int phase, void* stream);
 
 /*
+ * Pre-MoE RMSNorm (decoder-layer glue in front of the block).  Replaces utils/UniMoE_Audio_model.py:240
+ * `hidden_states = self.post_attention_layernorm(hidden_states)` (Qwen2RMSNorm, model.py:207, eps = rms_norm_eps):
+ * y = D(weight * D(float(x) * rsqrt(mean(float(x)^2) + eps))).  One pass: 2 x T x H x sizeof(D) bytes of HBM traffic.
+ * Together with `residual` of dcmoe_combine this covers model.py:239-242 around the MoE call.
+ *   x, out       [T, H] D (out may not alias x: the caller keeps x as the residual)
+ *   weight       [H] D
+ */
+int dcmoe_rmsnorm(const void* x, const void* weight, double eps, int64_t T, const dcmoe_config* cfg, void* out,
+                  void* stream);
+
+/*
  * Combine.  Replaces core.py:486-488 + utils/UniMoE_Audio_utils.py:488-523 (decompress_matrix + "se,sem->sm"
  * einsum), core.py:338-353 (zeros + adds of routed and shared outputs): per token, a gather of the shared
  * row and of its <= n_real routed rows, fp32 accumulate in fixed order (deterministic, no atomics).

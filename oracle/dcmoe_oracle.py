@@ -16,6 +16,9 @@ Follows, function by function (paths relative to the reference tree):
   routed experts (SwiGLU FFN) ............. core.py:406-416, :48-49
   combine (decompress + einsum) ........... utils/UniMoE_Audio_utils.py:488-523, core.py:486-488
   shared experts .......................... core.py:344-351, :30-31
+  decoder-layer glue (rmsnorm, residual) .. utils/UniMoE_Audio_model.py:239-242; Qwen2RMSNorm.forward of the
+                                            reference's pinned dependency transformers (model.py:54, :207), pinned by
+                                            tests/golden/glue_*.npz (tools/make_golden_glue.py)
 
 Differences from the reference *implementation* (not its results): rows are gathered per expert
 with ``index_select`` in ascending token order (the canonical stable permutation of SURVEY.md
@@ -152,3 +155,23 @@ def forward(hidden_states: torch.Tensor, weights: Dict[str, torch.Tensor], atten
                      weights[SHARED.format(e=e, proj="down_proj")].to(D))
             final = final + y * gw[:, n_dyn + e, None]
     return OracleOutput(final.reshape(B, S, H), logits, top_k, mask, gw, aux, counts, perm)
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """post_attention_layernorm (reference model.py:240): transformers Qwen2RMSNorm.forward restated --
+    fp32 mean of squares, rsqrt, cast to the layer dtype, multiply by the weight in the layer dtype."""
+    dt = x.dtype
+    xf = x.to(torch.float32)
+    var = xf.pow(2).mean(-1, keepdim=True)
+    n = (xf * torch.rsqrt(var + eps)).to(dt)
+    return weight * n
+
+
+def glue_forward(hidden_states: torch.Tensor, norm_weight: torch.Tensor, weights: Dict[str, torch.Tensor],
+                 attention_mask: Optional[torch.Tensor] = None, eps: float = 1e-6, cfg: dict | None = None,
+                 logits: Optional[torch.Tensor] = None):
+    """Second half of the decoder layer (reference model.py:239-242): residual + mlp(rmsnorm(h)).
+    Returns (hidden_states_out, OracleOutput of the MoE call)."""
+    n = rmsnorm(hidden_states, norm_weight, eps)
+    o = forward(n, weights, attention_mask, cfg, logits=logits)
+    return hidden_states + o.final_hidden_states.reshape(hidden_states.shape), o

@@ -65,6 +65,25 @@ def test_layer_oracle_matches_reference_golden(dname, golden_dir):
     assert t[0].shape == (1, 512, 2048) and t[5].dim() == 0
 
 
+@pytest.mark.parametrize("dname", ["fp32", "bf16"])
+def test_glue_oracle_matches_reference_golden(dname, golden_dir):
+    """rmsnorm + MoE + residual (model.py:239-242) against the reference block + transformers' Qwen2RMSNorm."""
+    g = np.load(os.path.join(golden_dir, f"glue_{dname}.npz"))
+    dt = DT[dname]
+    W = O.make_weights(seed=int(g["weight_seed"]), dtype=dt)
+    x = (torch.randn(1, 128, 2048, generator=torch.Generator().manual_seed(int(g["x_seed"]))) * float(g["x_scale"])).to(dt)
+    nw = (1.0 + 0.1 * torch.randn(2048, generator=torch.Generator().manual_seed(int(g["norm_weight_seed"])))).to(dt)
+    n = O.rmsnorm(x, nw, float(g["eps"]))
+    assert n.dtype == dt
+    assert np.array_equal(n.float().reshape(128, 2048)[::4].numpy(), g["normed_rows"])      # same torch ops: bit-exact
+    final, o = O.glue_forward(x, nw, W, eps=float(g["eps"]))
+    assert np.array_equal(o.full_router_logits.float().numpy(), g["full_router_logits"])
+    assert np.array_equal(o.expert_mask.numpy(), g["expert_mask"])
+    rtol = 1e-5 if dname == "fp32" else 1e-2
+    scale = float(np.abs(g["final_rows"]).max())
+    np.testing.assert_allclose(final.float().reshape(128, 2048)[::4].numpy(), g["final_rows"], rtol=rtol, atol=rtol * scale)
+
+
 def test_route_edge_cases():
     # empty input, single token, all-equal logits (exact 9-way tie -> lowest indices win)
     top_k, mask, gw, aux = R.route(torch.zeros(0, 11))

@@ -5,7 +5,7 @@ Only what the hot path needs lives here: ``csrc/`` (hand-written sm_100a CUDA + 
 ``include/dcmoe_b200.h``), ``ops`` (torch-facing wrappers that pass device pointers and the current
 stream through ctypes) and ``dcmoe`` (the host-side mirror of the reference module interface).
 """
-from .dcmoe import DCMoE, UniMoEAudioSparseMoeBlock  # noqa: F401
+from .dcmoe import DCMoE, PostAttentionMoE, UniMoEAudioSparseMoeBlock  # noqa: F401
 from .ops import LayerDims, Workspace  # noqa: F401
 
-__all__ = ["DCMoE", "UniMoEAudioSparseMoeBlock", "LayerDims", "Workspace"]
+__all__ = ["DCMoE", "PostAttentionMoE", "UniMoEAudioSparseMoeBlock", "LayerDims", "Workspace"]

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdcmoe_b200.so")
-SOURCES = ["api.cu", "router.cu", "plan_permute_combine.cu", "ffn_simt.cu", "ffn_tcgen05.cu", "ffn_tcgen05_2cta.cu", "ffn_tcgen05_stream.cu", "ep.cu"]
+SOURCES = ["api.cu", "router.cu", "plan_permute_combine.cu", "ffn_simt.cu", "ffn_tcgen05.cu", "ffn_tcgen05_2cta.cu", "ffn_tcgen05_stream.cu", "rmsnorm.cu", "ep.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(HERE, "..", "include", "dcmoe_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libdcmoe_b200.so (declared in include/dcmoe_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda.h>
@@ -147,11 +148,20 @@ int launch_ffn_simt(const void*, const void*, const void*, const void*, const fl
                     const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                        const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+int launch_rmsnorm(const void*, const void*, double, int64_t, const dcmoe_config*, void*, cudaStream_t);
 bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int);
 int launch_ffn_tcgen05_stream(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                               const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                             const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("DCMOE_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 static int require_device() {
     int n = 0;
@@ -311,6 +321,15 @@ int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_
     DCMOE_PROLOGUE(T)
     if (T > 0 && (!y || !slot_of || !out)) { set_error("dcmoe_combine: NULL pointer argument"); return DCMOE_ERR_INVALID; }
     return launch_combine(y, slot_of, T, cfg, residual, out, (cudaStream_t)stream);
+}
+
+int dcmoe_rmsnorm(const void* x, const void* weight, double eps, int64_t T, const dcmoe_config* cfg, void* out,
+                  void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!x || !weight || !out)) { set_error("dcmoe_rmsnorm: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    if (T > 0 && x == out) { set_error("dcmoe_rmsnorm: out must not alias x (x stays the residual)"); return DCMOE_ERR_INVALID; }
+    if (!(eps >= 0.0)) { set_error("dcmoe_rmsnorm: eps must be >= 0"); return DCMOE_ERR_INVALID; }
+    return launch_rmsnorm(x, weight, eps, T, cfg, out, (cudaStream_t)stream);
 }
 
 int dcmoe_pack_expert(const void* gate_proj, const void* up_proj, const void* down_proj, int group, int part,

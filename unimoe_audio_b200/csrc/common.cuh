@@ -21,6 +21,29 @@ int validate_config(const dcmoe_config* cfg);
 // 128B swizzle (api.cu)
 int make_tensor_map_bf16(void* map, const void* base, int64_t rows, int64_t cols, int box_rows);
 
+// Programmatic dependent launch (decode-sized chain front_small -> GEMM-1 -> GEMM-2 -> combine): the next kernel's
+// CTAs may become resident and run their prologue (barrier init, TMEM allocation, tensor-map prefetch) while the
+// previous kernel is still running; every such kernel executes grid_dep_wait() before its first global-memory
+// access, which returns once the preceding grid has completed and its writes are visible.  DCMOE_PDL=0 disables.
+bool pdl_enabled();   // api.cu
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
@@ -58,6 +81,9 @@ inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
 
 // ---- device helpers ----
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // c10::BFloat16 rounding (round-to-nearest-even) on an fp32 value, kept in fp32
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_vec = H * ESIZE / 16;
     const int64_t row_bytes = (int64_t)H * ESIZE;
+    grid_dep_wait();   // (decode-sized calls launch this kernel programmatically dependent on GEMM-2; else a no-op)
     for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < T; t += (int64_t)gridDim.x * 8) {   // grid may be capped
     // compact source list, in accumulation order: lane i < n_src holds the base pointer of source row i
     // (selected routed rows in expert order, then the shared row)
@@ -379,14 +380,16 @@ int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe
     EpPeers peers{};
     peers.y[0] = (const char*)y;
     dim3 grid((unsigned)ceil_div(T, 8)), block(256);
+    const bool pdl = pdl_enabled() && T <= 64;   // decode-sized chain: come up under the tail of GEMM-2
     if (cfg->dtype == DCMOE_BF16)
-        ep_combine_kernel<true, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
-                                                               cfg->n_real, cfg->n_real, nullptr, (const char*)residual, (char*)out);
-    else
-        ep_combine_kernel<false, 0><<<grid, block, 0, stream>>>((const char*)y, peers, slot_of, T, cfg->hidden_size,
-                                                                cfg->n_real, cfg->n_real, nullptr, (const char*)residual,
-                                                                (char*)out);
-    return check_cuda(cudaGetLastError(), "combine kernel launch");
+        return check_cuda(launch_kernel(ep_combine_kernel<true, 0>, grid, block, 0, stream, pdl, (const char*)y, peers, slot_of, T,
+                                        cfg->hidden_size, cfg->n_real, cfg->n_real, (float*)nullptr, (const char*)residual,
+                                        (char*)out),
+                          "combine kernel launch");
+    return check_cuda(launch_kernel(ep_combine_kernel<false, 0>, grid, block, 0, stream, pdl, (const char*)y, peers, slot_of, T,
+                                    cfg->hidden_size, cfg->n_real, cfg->n_real, (float*)nullptr, (const char*)residual,
+                                    (char*)out),
+                      "combine kernel launch");
 }
 
 }  // namespace dcmoe

@@ -157,6 +157,10 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    // everything above touched no global memory: under programmatic dependent launch it overlapped the tail of the
+    // previous kernel; now wait for it (plan / x_packed / h are its outputs) and let the next kernel's CTAs come up
+    grid_dep_wait();
+    grid_dep_launch();
     const long long t_start = p.dbg ? clock64() : 0;
     const Segment sg = cta_segment(*p.n_mtiles, p.gpg);
     // The WEIGHTS are the MMA's M operand (128 rows = 8 granules per M-tile) and the token rows its N operand
@@ -438,10 +442,16 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     }
     dim3 grid((unsigned)n_ctas), block(NUM_THREADS);
     if (phase != 2) {
-        ffn_stream_kernel<true><<<grid, block, SMEM_BYTES, stream>>>(m_x, m_xp, m_w13[0], m_w13[1], m_w13[2], m_w13[3], p1);
-        if ((rc = check_cuda(cudaGetLastError(), "ffn_stream_kernel<SwiGLU> launch"))) return rc;
+        if ((rc = check_cuda(launch_kernel(ffn_stream_kernel<true>, grid, block, SMEM_BYTES, stream, pdl_enabled(), m_x, m_xp,
+                                           m_w13[0], m_w13[1], m_w13[2], m_w13[3], p1),
+                             "ffn_stream_kernel<SwiGLU> launch")))
+            return rc;
     }
-    if (phase != 1) ffn_stream_kernel<false><<<grid, block, SMEM_BYTES, stream>>>(m_h, m_h, m_w2[0], m_w2[1], m_w2[2], m_w2[3], p2);
+    if (phase != 1 &&
+        (rc = check_cuda(launch_kernel(ffn_stream_kernel<false>, grid, block, SMEM_BYTES, stream, pdl_enabled(), m_h, m_h,
+                                       m_w2[0], m_w2[1], m_w2[2], m_w2[3], p2),
+                         "ffn_stream_kernel<down> launch")))
+        return rc;
     if (debug) {   // tuning only: synchronises
         static int printed = 0;
         cudaStreamSynchronize(stream);

@@ -787,6 +787,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = NE ? NE : rc.E;
     const int n_dyn = NDYN ? NDYN : rc.n_dyn;
+    grid_dep_launch();   // the GEMM-1 CTAs may come up on the other SMs and run their prologue meanwhile
     // ---- phase 1: gate projection, warp = (token block of 16, K eighth) ----
     {
         const int blk = warp >> 3, ks = warp & 7;

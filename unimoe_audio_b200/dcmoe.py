@@ -283,5 +283,51 @@ class DCMoE(nn.Module):
         return out, logits, top_k, mask, gw, aux
 
 
+class PostAttentionMoE(nn.Module):
+    """Host mirror of the second half of the reference decoder layer (utils/UniMoE_Audio_model.py:239-242):
+
+        residual = h;  h = self.post_attention_layernorm(h);  h, *router = self.mlp(h, mask, aux_w);  h = residual + h
+
+    with the same sub-module names (``post_attention_layernorm.weight``, ``mlp.*``), so a decoder layer's state dict
+    loads into it unchanged.  The RMSNorm is one HBM pass (``dcmoe_rmsnorm``) and the residual add is fused into the
+    combine pass (``dcmoe_combine(residual=...)``): no separate elementwise kernels run around the MoE block.
+    Returns the 6-tuple of the MoE block with ``hidden_states`` already holding ``residual + mlp(norm(h))``.
+    """
+
+    class _Norm(nn.Module):
+        def __init__(self, hidden_size: int, eps: float):
+            super().__init__()
+            self.weight = nn.Parameter(torch.ones(hidden_size))
+            self.variance_epsilon = eps
+
+    def __init__(self, config, mlp: Optional["DCMoE"] = None):
+        super().__init__()
+        cfg = config if isinstance(config, dict) else config.__dict__
+        self.mlp = mlp if mlp is not None else DCMoE(config)
+        self.post_attention_layernorm = PostAttentionMoE._Norm(self.mlp.hidden_dim, float(cfg.get("rms_norm_eps", 1e-6)))
+
+    @classmethod
+    def from_reference_layer(cls, layer: nn.Module) -> "PostAttentionMoE":
+        """Build from a reference decoder layer (model.py:196-247): takes its ``mlp`` and ``post_attention_layernorm``."""
+        mlp = layer.mlp if isinstance(layer.mlp, DCMoE) else DCMoE.from_reference(layer.mlp)
+        eps = float(layer.post_attention_layernorm.variance_epsilon)
+        m = cls({"rms_norm_eps": eps}, mlp=mlp)
+        w = layer.post_attention_layernorm.weight.detach()
+        m.post_attention_layernorm.weight = nn.Parameter(w.clone().to(mlp.gate.weight.device), requires_grad=False)
+        return m.eval()
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, padding_token_mask: Optional[torch.Tensor] = None,
+                aux_balance_weight: Optional[torch.Tensor] = None):
+        if not hidden_states.is_cuda:
+            raise RuntimeError("PostAttentionMoE.forward needs CUDA tensors: there is no CPU fallback")
+        x = hidden_states if hidden_states.is_contiguous() else hidden_states.contiguous()
+        w = self.post_attention_layernorm.weight.detach()
+        if w.dtype != x.dtype:
+            raise TypeError(f"hidden_states dtype {x.dtype} != norm weight dtype {w.dtype}")
+        normed = ops.rmsnorm(x, w, self.post_attention_layernorm.variance_epsilon, self.mlp.dims)
+        return self.mlp(normed, padding_token_mask, aux_balance_weight, residual=x)
+
+
 # The reference's class name, so `utils.UniMoE_Audio_model.UniMoEAudioSparseMoeBlock = ...` reads naturally.
 UniMoEAudioSparseMoeBlock = DCMoE

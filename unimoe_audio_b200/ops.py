@@ -184,6 +184,20 @@ def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] =
                "dcmoe_combine")
 
 
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, out: Optional[torch.Tensor] = None):
+    """Qwen2RMSNorm of [T, H] rows (the decoder layer's post_attention_layernorm, model.py:240)."""
+    lib = _lib.load()
+    if not (x.is_cuda and weight.is_cuda and x.is_contiguous() and weight.is_contiguous() and x.dtype == weight.dtype):
+        raise ValueError("rmsnorm needs contiguous CUDA tensors of one dtype")
+    if x.shape[-1] != dims.hidden_size or weight.numel() != dims.hidden_size:
+        raise ValueError("rmsnorm: hidden size mismatch")
+    out = torch.empty_like(x) if out is None else out
+    T = x.numel() // dims.hidden_size
+    _lib.check(lib.dcmoe_rmsnorm(_ptr(x), _ptr(weight), float(eps), T, dims.c_config(x.dtype), _ptr(out), _stream()),
+               "dcmoe_rmsnorm")
+    return out
+
+
 def pack_expert(gate_proj: torch.Tensor, up_proj: torch.Tensor, down_proj: torch.Tensor, group: int, part: int,
                 dims: LayerDims, w13: torch.Tensor, w2: torch.Tensor):
     lib = _lib.load()
