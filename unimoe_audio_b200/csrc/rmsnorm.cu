@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const char* __restrict__ x
     const int n_vec = H * ESIZE / 16;          // 16-byte vectors per row (H % 256 == 0 -> a multiple of 32)
     const int per_lane = n_vec >> 5;
     const int64_t row_bytes = (int64_t)H * ESIZE;
-    grid_dep_wait();
+    grid_dep_wait();     // decode-sized calls chain this kernel and the router front end programmatically
+    grid_dep_launch();
     for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < T; t += (int64_t)gridDim.x * 8) {
         const char* xr = x + t * row_bytes + lane * 16;
         char* yr = out + t * row_bytes + lane * 16;
@@ -100,13 +101,14 @@ int launch_rmsnorm(const void* x, const void* weight, double eps, int64_t T, con
     if (T == 0) return DCMOE_OK;
     const int64_t blocks = std::min<int64_t>(ceil_div(T, 8), 148 * 8 * 4);
     dim3 grid((unsigned)blocks), block(256);
+    const bool pdl = pdl_enabled() && T <= 64;
     if (cfg->dtype == DCMOE_BF16)
-        rmsnorm_kernel<true><<<grid, block, 0, stream>>>((const char*)x, (const char*)weight, (float)eps, T, cfg->hidden_size,
-                                                         (char*)out);
-    else
-        rmsnorm_kernel<false><<<grid, block, 0, stream>>>((const char*)x, (const char*)weight, (float)eps, T, cfg->hidden_size,
-                                                          (char*)out);
-    return check_cuda(cudaGetLastError(), "rmsnorm kernel launch");
+        return check_cuda(launch_kernel(rmsnorm_kernel<true>, grid, block, 0, stream, pdl, (const char*)x, (const char*)weight,
+                                        (float)eps, T, cfg->hidden_size, (char*)out),
+                          "rmsnorm kernel launch");
+    return check_cuda(launch_kernel(rmsnorm_kernel<false>, grid, block, 0, stream, pdl, (const char*)x, (const char*)weight,
+                                    (float)eps, T, cfg->hidden_size, (char*)out),
+                      "rmsnorm kernel launch");
 }
 
 }  // namespace dcmoe

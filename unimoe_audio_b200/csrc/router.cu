@@ -787,6 +787,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = NE ? NE : rc.E;
     const int n_dyn = NDYN ? NDYN : rc.n_dyn;
+    grid_dep_wait();     // (launched programmatically dependent on whatever precedes it, e.g. dcmoe_rmsnorm)
     grid_dep_launch();   // the GEMM-1 CTAs may come up on the other SMs and run their prologue meanwhile
     // ---- phase 1: gate projection, warp = (token block of 16, K eighth) ----
     {
@@ -1074,15 +1075,19 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     rc.plus_eps = r(1e-6f);
     rc.finfo_min = -3.3895313892515355e38f;
     rc.always_softmax = 0;
+    const dim3 grid(1), block(1024);
+    cudaError_t err;
     if (rc.n_dyn == 9 && rc.E == 11)
-        front_small_kernel<9, 11><<<1, 1024, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask,
-            (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad, (int)sz.max_mtiles, (__nv_bfloat16*)logits_out, top_k,
-            expert_mask, (__nv_bfloat16*)global_weight, pv, (__nv_bfloat16*)x_packed, slot_of, row_token, row_scale);
+        err = launch_kernel(front_small_kernel<9, 11>, grid, block, 0, stream, pdl_enabled(), (const __nv_bfloat16*)x,
+                            (const __nv_bfloat16*)w_gate, attn_mask, (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad,
+                            (int)sz.max_mtiles, (__nv_bfloat16*)logits_out, top_k, expert_mask, (__nv_bfloat16*)global_weight, pv,
+                            (__nv_bfloat16*)x_packed, slot_of, row_token, row_scale);
     else
-        front_small_kernel<0, 0><<<1, 1024, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask,
-            (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad, (int)sz.max_mtiles, (__nv_bfloat16*)logits_out, top_k,
-            expert_mask, (__nv_bfloat16*)global_weight, pv, (__nv_bfloat16*)x_packed, slot_of, row_token, row_scale);
-    return check_cuda(cudaGetLastError(), "front_small_kernel launch");
+        err = launch_kernel(front_small_kernel<0, 0>, grid, block, 0, stream, pdl_enabled(), (const __nv_bfloat16*)x,
+                            (const __nv_bfloat16*)w_gate, attn_mask, (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad,
+                            (int)sz.max_mtiles, (__nv_bfloat16*)logits_out, top_k, expert_mask, (__nv_bfloat16*)global_weight, pv,
+                            (__nv_bfloat16*)x_packed, slot_of, row_token, row_scale);
+    return check_cuda(err, "front_small_kernel launch");
 }
 
 }  // namespace dcmoe

@@ -266,10 +266,13 @@ class DCMoE(nn.Module):
                 ops.permute(x, mask, gw, ws)
                 hook("permute")
             impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
-            ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
-            hook("ffn_gemm1")
-            ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)
-            hook("ffn_gemm2")
+            if self.stage_hook is None:
+                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=0)     # both GEMMs, one call
+            else:
+                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
+                hook("ffn_gemm1")
+                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)
+                hook("ffn_gemm2")
             res = None
             if residual is not None:      # extension: fuse the decoder layer's residual add (model.py:242)
                 if residual.shape != hidden_states.shape or residual.dtype != dt:
