@@ -243,16 +243,19 @@ def run_ours(args):
         layer.comm_events.clear()
     if rank == 0:
         sampler.mark_begin()
-    step_ev = []
+    step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    import gc
+    gc.collect()
+    gc.disable()                 # a collection pause in the enqueue loop starves the GPU for several steps
     host_t0 = time.perf_counter()
     for i in range(args.steps):
         stage_events.append([])
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s, e = step_ev[i]
         s.record()
         out = layer(xs[(args.warmup + i) % n_rot], None, None)
         e.record()
-        step_ev.append((s, e))
     host_ms_per_step = (time.perf_counter() - host_t0) * 1e3 / args.steps   # enqueue time only (no sync)
+    gc.enable()
     barrier()
     if rank == 0:
         sampler.mark_end()

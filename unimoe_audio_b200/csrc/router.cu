@@ -619,12 +619,12 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
     if (warp == 0) {
         // the producer puts the first stages in flight before anyone stages W_g
         for (int blk = blockIdx.x; blk < n_blocks && prod_it < kXStages; blk += gridDim.x, ++prod_it) {
-            if (lane == 0) {
-                mbar_expect_tx(x_full(prod_it), (uint32_t)(kRouterBlock * H * 2));
-                for (int c = 0; c < n_chunks; ++c)
-                    tma_load_2d(xs + prod_it * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
-                                x_full(prod_it));
-            }
+            // one box per lane: a TMA issue costs the issuing thread ~50 cycles (tools/probe_stream.cu)
+            if (lane == 0) mbar_expect_tx(x_full(prod_it), (uint32_t)(kRouterBlock * H * 2));
+            __syncwarp();
+            for (int c = lane; c < n_chunks; c += 32)
+                tma_load_2d(xs + prod_it * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
+                            x_full(prod_it));
             __syncwarp();
         }
     } else {
@@ -656,12 +656,11 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const int st = it & (kXStages - 1);
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
             mbar_wait(x_empty(st), ph ^ 1u);
-            if (lane == 0) {
-                mbar_expect_tx(x_full(st), (uint32_t)(kRouterBlock * H * 2));
-                for (int c = 0; c < n_chunks; ++c)
-                    tma_load_2d(xs + st * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
-                                x_full(st));
-            }
+            if (lane == 0) mbar_expect_tx(x_full(st), (uint32_t)(kRouterBlock * H * 2));
+            __syncwarp();
+            for (int c = lane; c < n_chunks; c += 32)
+                tma_load_2d(xs + st * kXStageBytes + c * (kRouterBlock * 128), &tmap_x, c * 64, blk * kRouterBlock,
+                            x_full(st));
             __syncwarp();
         }
     } else if (warp <= 4) {

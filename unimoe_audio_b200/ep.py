@@ -155,6 +155,15 @@ class ExpertParallelDCMoE:
                             ex.down_proj.weight.detach().contiguous(), self.n_loc, i, ld, w13, w2)
         self._w13, self._w2 = w13, w2
 
+    def set_packed_local_weights(self, w13: torch.Tensor, w2: torch.Tensor):
+        """Use packs built elsewhere (``checkpoint.load_dcmoe_ep``: this rank's experts read straight from a
+        checkpoint) instead of packing from the wrapped module's parameters."""
+        d, G = self.m.dims, self.n_loc + 1
+        if tuple(w13.shape) != (G, 2 * d.dynamic_intermediate_size, d.hidden_size) or \
+                tuple(w2.shape) != (G, d.hidden_size, d.dynamic_intermediate_size) or not (w13.is_cuda and w2.is_cuda):
+            raise ValueError("packed local weights have the wrong shape for this rank's expert count")
+        self._w13, self._w2 = w13.contiguous(), w2.contiguous()
+
     def default_row_capacity(self, T: int, T_global: int) -> int:
         t_pad = (T + 127) // 128 * 128
         return t_pad + self.n_loc * T_global + 128 * self.n_loc
