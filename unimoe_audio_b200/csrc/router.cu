@@ -105,6 +105,7 @@ struct RouteConsts {
     float thr_p, thr_eps, plus_eps, finfo_min;
     int n_dyn, E;
     int always_softmax;   // debug: evaluate the mixer softmax even when it is provably 1 (DCMOE_ROUTER_ALWAYS_SOFTMAX=1)
+    unsigned long long* dbg;   // tuning (DCMOE_ROUTER_DEBUG=1): per-CTA cycle counters of router_tma_kernel, else nullptr
 };
 
 // exp of the canonical arithmetic for dtype D
@@ -524,6 +525,7 @@ router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
             int raw, mk;
             float gw, ga;
             route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            const long long q2 = rc.dbg ? clock64() : 0;
             if (valid && j < E) {
                 logits_out[t * E + j] = __float2bfloat16_rn(l);
                 gw_out[t * E + j] = __float2bfloat16_rn(gw);
@@ -615,6 +617,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         fence_barrier_init();
     }
     __syncthreads();   // barriers initialised
+    const long long t_begin = rc.dbg ? clock64() : 0;
     int prod_it = 0;
     if (warp == 0) {
         // the producer puts the first stages in flight before anyone stages W_g
@@ -631,23 +634,58 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         // W_g -> smem in mma B-fragment order (done by the 20 non-producer warps while the first x blocks are in
         // flight): wf[k16][nt][lane] = {W[n][16 k16 + 2 tq .. +1], W[n][16 k16 + 8 + 2 tq .. +1]}, n = 8 nt + lane / 4,
         // tq = lane % 4; rows n >= E are zero.  One 16-byte load (8 consecutive k of one row) feeds four entries.
-        const int n_kc = H >> 3;                       // 16-byte chunks per row
-        for (int i = tid - 32; i < 16 * n_kc; i += kTmaThreads - 32) {
-            const int n = i / n_kc, kc = i - n * n_kc;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (n < E) v = ld_ca_v4(wg + (int64_t)n * H + kc * 8);
-            if (n >= E) continue;
-            const int k16 = kc >> 1, hi = kc & 1, g = n & 7;
-            uint32_t* dst = n < 8 ? reinterpret_cast<uint32_t*>(wf0) + ((k16 * 32 + g * 4) << 1) + hi
-                                  : reinterpret_cast<uint32_t*>(wf1) + ((k16 * L1 + g * 4) << 1) + hi;
-            dst[0] = v.x;
-            dst[2] = v.y;
-            dst[4] = v.z;
-            dst[6] = v.w;
+        // One item = (row n, k16): 32 contiguous bytes of W_g -> the four (tq) 8-byte entries of that row, which are
+        // contiguous in the fragment array, written as two 128-bit stores.  Consecutive threads take consecutive
+        // rows of one k16, so a warp writes 1 KB contiguous: no bank conflicts (the former 4-byte scatter was
+        // 16-way conflicted and took 5,400 cycles = 15 % of the kernel).
+        const int n_k16 = H >> 4;
+        const int ng0 = E < 8 ? E : 8, ng1 = E > 8 ? E - 8 : 0;
+        const int n0_items = ng0 * n_k16, n_items = (ng0 + ng1) * n_k16;
+        constexpr int kStageUnroll = 2;
+        for (int i0 = tid - 32; i0 < n_items; i0 += kStageUnroll * (kTmaThreads - 32)) {
+            uint4 v0[kStageUnroll], v1[kStageUnroll];
+            uint4* dst[kStageUnroll];
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int i = i0 + u * (kTmaThreads - 32);
+                dst[u] = nullptr;
+                if (i >= n_items) continue;
+                int n, k16;
+                if (i < n0_items) {
+                    k16 = i / ng0;
+                    n = i - k16 * ng0;
+                    dst[u] = reinterpret_cast<uint4*>(wf0 + k16 * 32 + n * 4);
+                } else {
+                    const int i1 = i - n0_items;
+                    k16 = i1 / ng1;
+                    n = 8 + i1 - k16 * ng1;
+                    dst[u] = reinterpret_cast<uint4*>(wf1 + k16 * L1 + (n - 8) * 4);
+                }
+                const __nv_bfloat16* src = wg + (int64_t)n * H + k16 * 16;
+                v0[u] = ld_ca_v4(src);
+                v1[u] = ld_ca_v4(src + 8);
+            }
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                if (dst[u] == nullptr) continue;
+                dst[u][0] = make_uint4(v0[u].x, v1[u].x, v0[u].y, v1[u].y);   // entries tq = 0, 1: {k 0..7 half, k 8..15 half}
+                dst[u][1] = make_uint4(v0[u].z, v1[u].z, v0[u].w, v1[u].w);   // entries tq = 2, 3
+            }
+        }
+        if (E < 8) {   // n-tile 0 rows E..7 must read as zero
+            for (int i = tid - 32; i < (8 - E) * n_k16; i += kTmaThreads - 32) {
+                const int k16 = i / (8 - E), n = E + i % (8 - E);
+                uint4* d = reinterpret_cast<uint4*>(wf0 + k16 * 32 + n * 4);
+                d[0] = d[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
     }
 
-    __syncthreads();   // W_g fragments staged
+    // W_g fragments staged: a barrier of the 28 consumer warps only -- the producer is still issuing its first 64
+    // boxes (~60 cycles each in the TMA unit) and needs nothing from this phase (barrier 0 is not used again)
+    if (warp != 0) named_bar_sync(0, kTmaThreads - 32);
+    const long long t_staged = rc.dbg ? clock64() : 0;
+    long long d0 = 0, d1 = 0, d2 = 0;
     constexpr int kFullCount = 128 + 256;   // gate warps + one routing group
     if (warp == 0) {
         // ================= TMA producer (continues after the stages issued above) =================
@@ -655,7 +693,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         for (int blk = blockIdx.x + prod_it * gridDim.x; blk < n_blocks; blk += gridDim.x, ++it) {
             const int st = it & (kXStages - 1);
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
+            const long long q0 = rc.dbg ? clock64() : 0;
             mbar_wait(x_empty(st), ph ^ 1u);
+            if (rc.dbg) d0 += clock64() - q0;
             if (lane == 0) mbar_expect_tx(x_full(st), (uint32_t)(kRouterBlock * H * 2));
             __syncwarp();
             for (int c = lane; c < n_chunks; c += 32)
@@ -676,7 +716,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
             const int rs = it % kRedStages;
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const long long q0 = rc.dbg ? clock64() : 0;
             mbar_wait(x_full(st), ph);
+            const long long q1 = rc.dbg ? clock64() : 0;
             for (int cc = 0; cc < chunks_per_warp; ++cc) {
                 const int c = wq * chunks_per_warp + cc;
                 const uint32_t tile = xs + st * kXStageBytes + c * (kRouterBlock * 128);
@@ -694,7 +736,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(x_empty(st));           // this warp is done reading the x stage
+            const long long q2 = rc.dbg ? clock64() : 0;
             if (it >= kRedStages) named_bar_sync(7 + rs, kFullCount);
+            if (rc.dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
             float* r = red + ((rs * 4 + wq) * kRouterBlock) * 16;
             r[g * 16 + 2 * tq] = c0[0];
             r[g * 16 + 2 * tq + 1] = c0[1];
@@ -705,6 +749,13 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             r[(g + 8) * 16 + 8 + 2 * tq] = c1[2];
             r[(g + 8) * 16 + 8 + 2 * tq + 1] = c1[3];
             named_bar_arrive(1 + rs, kFullCount);
+        }
+        if (rc.dbg && warp == 1 && lane == 0) {
+            rc.dbg[blockIdx.x * 16 + 2] = d0;
+            rc.dbg[blockIdx.x * 16 + 3] = d1;
+            rc.dbg[blockIdx.x * 16 + 4] = d2;
+            rc.dbg[blockIdx.x * 16 + 10] = it;
+            rc.dbg[blockIdx.x * 16 + 11] = clock64() - t_begin;   // gate warps done
         }
     } else {
         // ================= routing warps: group g = warps 5+8g .. 12+8g =================
@@ -720,7 +771,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const int tl = rw_ * 2 + half;
             const int64_t t = tok0 + tl;
             const bool valid = t < T;
+            const long long q0 = rc.dbg ? clock64() : 0;
             named_bar_sync(1 + rs, kFullCount);
+            const long long q1 = rc.dbg ? clock64() : 0;
             float l = 0.0f;
             if (j < E) {
                 const float* r = red + (rs * 4 * kRouterBlock + tl) * 16 + j;
@@ -732,6 +785,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             int raw, mk;
             float gw, ga;
             route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            const long long q2 = rc.dbg ? clock64() : 0;
             if (valid && j < E) {
                 logits_out[t * E + j] = __float2bfloat16_rn(l);
                 gw_out[t * E + j] = __float2bfloat16_rn(gw);
@@ -755,7 +809,19 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                 block_counts[(int64_t)blk * n_dyn + gtid] = c;
                 block_probs[(int64_t)blk * n_dyn + gtid] = pr;
             }
+            if (rc.dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
         }
+        if (rc.dbg && warp == 5 && lane == 0) {
+            rc.dbg[blockIdx.x * 16 + 5] = d0;
+            rc.dbg[blockIdx.x * 16 + 6] = d1;
+            rc.dbg[blockIdx.x * 16 + 7] = d2;
+            rc.dbg[blockIdx.x * 16 + 8] = clock64() - t_begin;   // routing group 0 done
+            rc.dbg[blockIdx.x * 16 + 9] = t_staged - t_begin;
+        }
+    }
+    if (rc.dbg && warp == 0 && lane == 0) {
+        rc.dbg[blockIdx.x * 16 + 0] = d0;
+        rc.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin;       // producer done
     }
 }
 
@@ -990,6 +1056,7 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         const char* dbg = getenv("DCMOE_ROUTER_ALWAYS_SOFTMAX");
         rc.always_softmax = (dbg && dbg[0] == '1') ? 1 : 0;
     }
+    rc.dbg = nullptr;
     const int64_t n_blocks = ceil_div(T, kRouterBlock);
     dim3 grid((unsigned)n_blocks), block(128);
 #define DCMOE_LAUNCH_ROUTER(BF, ND, NE_)                                                                              \
@@ -1024,6 +1091,13 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         int rc2 = make_tensor_map_bf16(&tmap, x, T, cfg->hidden_size, kRouterBlock);
         if (rc2) return rc2;
         dim3 g2((unsigned)(n_blocks < sms ? n_blocks : sms)), b2(kTmaThreads);
+        static unsigned long long* dbg = nullptr;
+        const bool debug = getenv("DCMOE_ROUTER_DEBUG") != nullptr;
+        if (debug) {
+            if (!dbg) cudaMalloc(&dbg, 256 * 16 * sizeof(unsigned long long));
+            cudaMemsetAsync(dbg, 0, 256 * 16 * sizeof(unsigned long long), stream);
+            rc.dbg = dbg;
+        }
         if (ref_shape)
             router_tma_kernel<9, 11><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
@@ -1032,6 +1106,20 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
             router_tma_kernel<0, 0><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
                 (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        if (debug) {   // tuning only: synchronises
+            static int printed = 0;
+            cudaStreamSynchronize(stream);
+            static unsigned long long host[256 * 16];
+            cudaMemcpy(host, dbg, sizeof(host), cudaMemcpyDeviceToHost);
+            if (printed++ < 4) {
+                double a[16] = {0};
+                for (unsigned c = 0; c < g2.x; ++c)
+                    for (int k = 0; k < 16; ++k) a[k] += (double)host[c * 16 + k] / g2.x;
+                fprintf(stderr, "router T=%lld blocks/CTA %.1f | staging %.0f | producer: wait-empty %.0f done@%.0f | gate warp: wait-x %.0f "
+                        "mma %.0f wait-red %.0f done@%.0f | routing grp0: wait-logits %.0f route %.0f store+stats %.0f done@%.0f (cycles)\n",
+                        (long long)T, a[10], a[9], a[0], a[1], a[2], a[3], a[4], a[11], a[5], a[6], a[7], a[8]);
+            }
+        }
         return check_cuda(cudaGetLastError(), "router_tma_kernel launch");
     }
     if (bf16 && logits_in == nullptr && ws_mode >= 1) {
@@ -1074,6 +1162,7 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     rc.plus_eps = r(1e-6f);
     rc.finfo_min = -3.3895313892515355e38f;
     rc.always_softmax = 0;
+    rc.dbg = nullptr;
     const dim3 grid(1), block(1024);
     cudaError_t err;
     if (rc.n_dyn == 9 && rc.E == 11)
