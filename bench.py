@@ -60,6 +60,9 @@ class ClockSampler:
         self.t_begin = self.t_end = None
 
     def start(self):
+        if os.environ.get("DCMOE_BENCH_NO_NVML"):      # diagnosis of launch stalls: run without the NVML thread
+            self.err = "disabled by DCMOE_BENCH_NO_NVML"
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -229,14 +232,17 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    out = None
     for i in range(args.warmup):
-        layer(xs[i % n_rot], None, None)
+        # `out` is kept alive across iterations exactly as in the timed loop: two output sets are live while a step
+        # is enqueued, so the caching allocator's second 64 MiB block (a cudaMalloc, 2-200 ms) is paid for here
+        out = layer(xs[i % n_rot], None, None)
     barrier()
 
     m.stage_hook = hook
     for i in range(2):           # untimed steps with the event hooks on (first-use costs of the hook path stay outside)
         stage_events.append([])
-        layer(xs[i % n_rot], None, None)
+        out = layer(xs[i % n_rot], None, None)
     barrier()
     stage_events.clear()
     if world > 1 and hasattr(layer, "comm_events"):
@@ -343,8 +349,11 @@ def run_ours(args):
     x_host = [x.cpu().pin_memory() for x in xs[:2]]
     pipe = HostPipeline(layer, depth=2, device=dev)
     e2e_steps = max(6, min(args.steps, 40))
-    for i in range(3):
+    for i in range(max(args.warmup, 3) + 3):    # warm-up with the timed loop's shape (two steps in flight): the caching
+        if len(pipe.pending) == pipe.depth:     # allocator then already owns every block the pipeline cycles through
+            pipe.result()
         pipe.submit(x_host[i % 2])
+    while pipe.pending:
         pipe.result()
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
