@@ -16,7 +16,8 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, layer: Callable, depth: int = 2, device: Optional[torch.device] = None):
+    def __init__(self, layer: Callable, depth: int = 3, device: Optional[torch.device] = None):
+        # depth >= 3 keeps H2D(i+2), compute(i+1) and D2H(i) in flight together; with 2 the next H2D waits for a D2H
         self.layer = layer
         self.depth = depth
         self.device = device or torch.device("cuda", torch.cuda.current_device())
