@@ -58,8 +58,8 @@ typedef struct dcmoe_config {
     int32_t dynamic_intermediate_size; /* 2752  */
     int32_t shared_intermediate_size;  /* 1376  (n_fix * shared == dynamic is required) */
     int32_t dtype;                     /* dcmoe_dtype */
-    int32_t reserved;                  /* keep the doubles 8-byte aligned; must be 0 */
-    double top_p;                      /* mlp_dynamic_top_p     0.7  (python float) */
+    int32_t fixed_top_k;               /* mlp_dynamic_top_k when top_p == 0 (fixed top-k routing, core.py:256-257), else 0 */
+    double top_p;                      /* mlp_dynamic_top_p     0.7  (python float); 0 selects fixed_top_k experts per token */
     double jitter_eps;                 /* router_jitter_noise   0.01 (python float) */
 } dcmoe_config;
 

@@ -109,7 +109,8 @@ def route(logits, attention_mask=None, cfg: dict | None = None):
     c.update(cfg or {})
     n_dyn = c["mlp_dynamic_expert_num"] + c["mlp_dynamic_null_expert_num"]
     return route_oracle_c.route(logits, attention_mask, n_dyn=n_dyn, n_fix=c["mlp_fixed_expert_num"],
-                                top_p=c["mlp_dynamic_top_p"], eps=c["router_jitter_noise"])
+                                top_p=c["mlp_dynamic_top_p"], eps=c["router_jitter_noise"],
+                                fixed_top_k=int(c.get("mlp_dynamic_top_k", 0) or 0))
 
 
 @torch.no_grad()
@@ -121,7 +122,6 @@ def forward(hidden_states: torch.Tensor, weights: Dict[str, torch.Tensor], atten
     """
     c = dict(DEFAULT_CONFIG)
     c.update(cfg or {})
-    assert c["mlp_dynamic_top_p"] != 0, "top-k mode (mlp_dynamic_top_p == 0) is not used by the reference config"
     B, S, H = hidden_states.shape
     D = hidden_states.dtype
     n_real = c["mlp_dynamic_expert_num"]

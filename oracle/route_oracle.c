@@ -135,9 +135,10 @@ static float row_sum8(const float* d, int n) {
  *   gw          [T, E] fp32 storage (D-rounded values)
  *   aux_out     [1] fp32  -- audio_load_balancing_loss_func with aux_balance_weight = None
  */
-int dcmoe_oracle_route(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
-                       int bf16, double top_p, double eps, int64_t* top_k, int32_t* mask, float* gw,
-                       float* aux_out) {
+/* fixed_k > 0: mlp_dynamic_top_p == 0 -- every token selects fixed_k (= mlp_dynamic_top_k) experts, core.py:256-257 */
+int dcmoe_oracle_route_k(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
+                         int bf16, double top_p, double eps, int fixed_k, int64_t* top_k, int32_t* mask, float* gw,
+                         float* aux_out) {
     const int E = n_dyn + n_fix;
     if (E > MAX_E || n_dyn < 1) return -1;
     const float thr_p = rnd((float)top_p, bf16);
@@ -166,6 +167,7 @@ int dcmoe_oracle_route(const float* logits, const int32_t* attn_mask, int64_t T,
             float c = rnd(run, bf16);          /* each prefix rounded to D    */
             if (!(c >= thr_p)) ++raw;          /* (~(c >= p)).sum() + 1       */
         }
+        if (fixed_k > 0) raw = fixed_k;        /* core.py:257: torch.full((T,), mlp_dynamic_top_k) */
         top_k[t] = raw;
         /* core.py:262 only visits groups 1..n_dyn: a token whose last prefix is still < p
          * (raw == n_dyn + 1, impossible for p <= 0.95) would select no expert at all. */
@@ -241,3 +243,9 @@ float dcmoe_oracle_exp_sleef(float x) { return exp_sleef_u10(x); }
 float dcmoe_oracle_exp_cr(float x) { return exp_cr(x); }
 float dcmoe_oracle_bf16_round(float x) { return bf16_round(x); }
 void dcmoe_oracle_softmax(const float* v, int n, int bf16, float* out) { softmax_D(v, n, bf16, out); }
+
+int dcmoe_oracle_route(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
+                       int bf16, double top_p, double eps, int64_t* top_k, int32_t* mask, float* gw,
+                       float* aux_out) {
+    return dcmoe_oracle_route_k(logits, attn_mask, T, n_dyn, n_fix, bf16, top_p, eps, 0, top_k, mask, gw, aux_out);
+}

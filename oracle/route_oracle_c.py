@@ -22,6 +22,11 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
             ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ]
+        _LIB.dcmoe_oracle_route_k.restype = ctypes.c_int
+        _LIB.dcmoe_oracle_route_k.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+            ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ]
         _LIB.dcmoe_oracle_exp_sleef.restype = ctypes.c_float
         _LIB.dcmoe_oracle_exp_sleef.argtypes = [ctypes.c_float]
         _LIB.dcmoe_oracle_exp_cr.restype = ctypes.c_float
@@ -30,12 +35,17 @@ def lib():
 
 
 def route(logits: torch.Tensor, attention_mask: torch.Tensor | None = None, n_dyn: int = 9, n_fix: int = 2,
-          top_p: float = 0.7, eps: float = 0.01):
+          top_p: float = 0.7, eps: float = 0.01, fixed_top_k: int = 0):
     """Route ``logits`` [T, n_dyn+n_fix] (fp32 or bf16, CPU).
 
     Returns (dynamic_top_k int64 [T], expert_mask int32 [T,E], global_weight D [T,E], aux_loss fp32 0-dim),
     the 3rd..6th entries of the reference block's return tuple (utils/UniMoE_Audio_core.py:358).
+    ``top_p == 0`` selects the fixed top-k branch (core.py:256-257) with ``fixed_top_k`` experts per token; the
+    reference then returns dynamic_top_k as int32.
     """
+    if top_p == 0 and fixed_top_k < 1:
+        raise ValueError("top_p == 0 needs fixed_top_k >= 1 (mlp_dynamic_top_k)")
+    fixed = int(fixed_top_k) if top_p == 0 else 0
     assert logits.dim() == 2 and logits.shape[1] == n_dyn + n_fix
     dt = logits.dtype
     assert dt in (torch.float32, torch.bfloat16)
@@ -49,11 +59,14 @@ def route(logits: torch.Tensor, attention_mask: torch.Tensor | None = None, n_dy
     mask = np.empty((T, E), dtype=np.int32)
     gw = np.empty((T, E), dtype=np.float32)
     aux = np.zeros((1,), dtype=np.float32)
-    rc = lib().dcmoe_oracle_route(
+    rc = lib().dcmoe_oracle_route_k(
         lg.ctypes.data, am.ctypes.data if am is not None else None, T, n_dyn, n_fix,
-        1 if dt == torch.bfloat16 else 0, float(top_p), float(eps),
+        1 if dt == torch.bfloat16 else 0, float(top_p), float(eps), fixed,
         top_k.ctypes.data, mask.ctypes.data, gw.ctypes.data, aux.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"dcmoe_oracle_route failed: {rc}")
-    return (torch.from_numpy(top_k), torch.from_numpy(mask), torch.from_numpy(gw).to(dt),
+    tk = torch.from_numpy(top_k)
+    if fixed:
+        tk = tk.to(torch.int32)
+    return (tk, torch.from_numpy(mask), torch.from_numpy(gw).to(dt),
             torch.tensor(float(aux[0]), dtype=torch.float32))

@@ -45,7 +45,8 @@ def test_query_sizes_reference_config():
 @pytest.mark.parametrize("bad", [
     dict(n_fix=3, shared_intermediate_size=1376),            # shared pack must equal the routed size
     dict(hidden_size=2000),                                   # H % 256
-    dict(top_p=0.0),                                          # fixed top-k mode not implemented
+    dict(top_p=0.0),                                          # fixed top-k mode needs fixed_top_k >= 1
+    dict(top_p=1.5),                                          # top_p outside [0, 1]
     dict(n_real=14, n_null=1, n_fix=2),                       # more than 16 router columns
 ])
 def test_invalid_configs_are_rejected_with_a_message(bad):
@@ -70,8 +71,11 @@ def test_module_mirrors_reference_interface():
     assert m.dynamic_real_moe.deepspeed_moe.ep_group is None
     with pytest.raises(NotImplementedError):
         DCMoE(dict(cfg, token_drop=True))
-    with pytest.raises(NotImplementedError):
-        DCMoE(dict(cfg, mlp_dynamic_top_p=0))
+    with pytest.raises(ValueError):
+        DCMoE(dict(cfg, mlp_dynamic_top_p=0))                      # fixed top-k routing needs mlp_dynamic_top_k >= 1
+    mk = DCMoE(dict(cfg, mlp_dynamic_top_p=0, mlp_dynamic_top_k=2))   # core.py:256-257
+    assert mk.dims.fixed_top_k == 2 and mk.dims.c_config(torch.bfloat16).fixed_top_k == 2
+    assert m.dims.c_config(torch.bfloat16).fixed_top_k == 0
 
 
 def test_no_cpu_fallback():

@@ -84,6 +84,36 @@ def test_glue_oracle_matches_reference_golden(dname, golden_dir):
     np.testing.assert_allclose(final.float().reshape(128, 2048)[::4].numpy(), g["final_rows"], rtol=rtol, atol=rtol * scale)
 
 
+@pytest.mark.parametrize("dname", ["fp32", "bf16"])
+@pytest.mark.parametrize("k", [2, 3])
+def test_fixed_topk_route_oracle_matches_reference_golden(dname, k, golden_dir):
+    """mlp_dynamic_top_p == 0 (core.py:254-257): every token selects mlp_dynamic_top_k experts; top_k is int32."""
+    g = np.load(os.path.join(golden_dir, f"routek_{dname}_k{k}.npz"))
+    for case in ("iid", "ties"):
+        lg = torch.from_numpy(g[f"{case}_logits"]).to(DT[dname])
+        am = torch.from_numpy(g["ties_attention_mask"]) if case == "ties" else None
+        top_k, mask, gw, aux = R.route(lg, am, top_p=0.0, fixed_top_k=k)
+        assert top_k.dtype == torch.int32 and np.array_equal(top_k.numpy(), g[f"{case}_dynamic_top_k"])
+        assert np.array_equal(mask.numpy(), g[f"{case}_expert_mask"])
+        assert np.array_equal(gw.float().numpy(), g[f"{case}_global_weight"])
+        np.testing.assert_allclose(aux.item(), float(g[f"{case}_aux_loss"]), rtol=1e-5)
+
+
+def test_fixed_topk_layer_oracle_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "layerk_bf16_k2.npz"))
+    dt = torch.bfloat16
+    W = O.make_weights(seed=int(g["weight_seed"]), dtype=dt)
+    x = torch.randn(1, 256, 2048, generator=torch.Generator().manual_seed(int(g["x_seed"]))).to(dt)
+    out = O.forward(x, W, cfg=dict(mlp_dynamic_top_p=0, mlp_dynamic_top_k=2))
+    assert np.array_equal(out.full_router_logits.float().numpy(), g["full_router_logits"])
+    assert out.dynamic_top_k.dtype == torch.int32 and np.array_equal(out.dynamic_top_k.numpy(), g["dynamic_top_k"])
+    assert np.array_equal(out.expert_mask.numpy(), g["expert_mask"])
+    assert np.array_equal(out.global_weight.float().numpy(), g["global_weight"])
+    final = out.final_hidden_states.float().reshape(256, 2048)
+    scale = float(np.abs(g["final_rows"]).max())
+    np.testing.assert_allclose(final[::4].numpy(), g["final_rows"], rtol=1e-2, atol=1e-2 * scale)
+
+
 def test_route_edge_cases():
     # empty input, single token, all-equal logits (exact 9-way tie -> lowest indices win)
     top_k, mask, gw, aux = R.route(torch.zeros(0, 11))

@@ -20,7 +20,7 @@ class DcmoeConfig(Structure):
     _fields_ = [
         ("hidden_size", c_int32), ("n_real", c_int32), ("n_null", c_int32), ("n_fix", c_int32),
         ("dynamic_intermediate_size", c_int32), ("shared_intermediate_size", c_int32),
-        ("dtype", c_int32), ("reserved", c_int32), ("top_p", c_double), ("jitter_eps", c_double),
+        ("dtype", c_int32), ("fixed_top_k", c_int32), ("top_p", c_double), ("jitter_eps", c_double),
     ]
 
 

@@ -54,9 +54,14 @@ int validate_config(const dcmoe_config* cfg) {
                   cfg->hidden_size, cfg->dynamic_intermediate_size, cfg->shared_intermediate_size);
         return DCMOE_ERR_UNSUPPORTED;
     }
-    if (!(cfg->top_p > 0.0)) {
-        set_error("mlp_dynamic_top_p == 0 (fixed top-k routing) is not supported; the reference config uses 0.7");
-        return DCMOE_ERR_UNSUPPORTED;
+    if (!(cfg->top_p >= 0.0) || cfg->top_p > 1.0) {
+        set_error("mlp_dynamic_top_p must lie in [0, 1] (got %g)", cfg->top_p);
+        return DCMOE_ERR_INVALID;
+    }
+    if (cfg->top_p == 0.0 ? cfg->fixed_top_k < 1 : cfg->fixed_top_k != 0) {
+        set_error("fixed_top_k must be >= 1 when top_p == 0 (core.py:256-257) and 0 otherwise (got top_p %g, fixed_top_k %d)",
+                  cfg->top_p, cfg->fixed_top_k);
+        return DCMOE_ERR_INVALID;
     }
     return DCMOE_OK;
 }

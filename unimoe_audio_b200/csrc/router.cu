@@ -104,6 +104,7 @@ __device__ __forceinline__ float row_sum8_lanes(float d, int n) {
 struct RouteConsts {
     float thr_p, thr_eps, plus_eps, finfo_min;
     int n_dyn, E;
+    int fixed_k;          // > 0: mlp_dynamic_top_p == 0, every token selects fixed_k dynamic experts (core.py:256-257)
     int always_softmax;   // debug: evaluate the mixer softmax even when it is provably 1 (DCMOE_ROUTER_ALWAYS_SOFTMAX=1)
     unsigned long long* dbg;   // tuning (DCMOE_ROUTER_DEBUG=1): per-CTA cycle counters of router_tma_kernel, else nullptr
 };
@@ -192,7 +193,7 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
         }
     }
     const bool below = dyn && !(rnd<BF16>(run) >= rc.thr_p);
-    const int raw = 1 + __popc(__ballot_sync(kFull, below) & half_mask);
+    const int raw = rc.fixed_k > 0 ? rc.fixed_k : 1 + __popc(__ballot_sync(kFull, below) & half_mask);
     raw_out = raw;
     const int k = raw <= n_dyn ? raw : 0;
     const int kmax = max(k, __shfl_xor_sync(kFull, k, 16));
@@ -1057,6 +1058,7 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         rc.always_softmax = (dbg && dbg[0] == '1') ? 1 : 0;
     }
     rc.dbg = nullptr;
+    rc.fixed_k = cfg->top_p == 0.0 ? cfg->fixed_top_k : 0;
     const int64_t n_blocks = ceil_div(T, kRouterBlock);
     dim3 grid((unsigned)n_blocks), block(128);
 #define DCMOE_LAUNCH_ROUTER(BF, ND, NE_)                                                                              \
@@ -1163,6 +1165,7 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     rc.finfo_min = -3.3895313892515355e38f;
     rc.always_softmax = 0;
     rc.dbg = nullptr;
+    rc.fixed_k = cfg->top_p == 0.0 ? cfg->fixed_top_k : 0;
     const dim3 grid(1), block(1024);
     cudaError_t err;
     if (rc.n_dyn == 9 && rc.E == 11)

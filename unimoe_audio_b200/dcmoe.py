@@ -125,9 +125,8 @@ class DCMoE(nn.Module):
         self.drop_token_num_print = g("drop_token_num_print", False)
         self.fp32_gate = g("fp32_gate", False)
         self.ep_size = g("ep_size", 1)
-        if self.mlp_dynamic_top_p == 0:
-            raise NotImplementedError("mlp_dynamic_top_p == 0 (fixed top-k routing, core.py:257) is not implemented; "
-                                      "the reference config uses top_p = 0.7")
+        if self.mlp_dynamic_top_p == 0 and not (1 <= int(self.mlp_dynamic_top_k or 0)):
+            raise ValueError("mlp_dynamic_top_p == 0 (fixed top-k routing, core.py:256-257) needs mlp_dynamic_top_k >= 1")
         if self.token_drop:
             raise NotImplementedError("token_drop=True (core.py:302-329) is not implemented; utils/config.json sets it False")
         if self.avg_hidden_states_last:
@@ -138,7 +137,8 @@ class DCMoE(nn.Module):
             hidden_size=self.hidden_dim, n_real=self.mlp_dynamic_real_expert_num, n_null=self.mlp_dynamic_null_expert_num,
             n_fix=self.mlp_fixed_expert_num, dynamic_intermediate_size=g("dynamic_intermediate_size"),
             shared_intermediate_size=g("shared_intermediate_size"), top_p=float(self.mlp_dynamic_top_p),
-            jitter_eps=float(self.router_jitter_noise))
+            jitter_eps=float(self.router_jitter_noise),
+            fixed_top_k=int(self.mlp_dynamic_top_k or 0) if self.mlp_dynamic_top_p == 0 else 0)
         # ---- parameters under the reference's names (core.py:220-222) ----
         self.gate = nn.Linear(self.hidden_dim, self.num_experts, bias=False)
         self.fixed_real_moe = nn.ModuleList(
@@ -283,6 +283,8 @@ class DCMoE(nn.Module):
             ops.combine(ws, out, res)
             hook("combine")
         aux = ws.aux_loss.clone().reshape(())
+        if self.mlp_dynamic_top_p == 0:
+            top_k = top_k.to(torch.int32)        # the reference builds it with torch.full(..., dtype=torch.int) (core.py:257)
         return out, logits, top_k, mask, gw, aux
 
 

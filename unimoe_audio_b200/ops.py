@@ -26,6 +26,7 @@ class LayerDims:
     shared_intermediate_size: int = 1376
     top_p: float = 0.7
     jitter_eps: float = 0.01
+    fixed_top_k: int = 0      # mlp_dynamic_top_k, used when top_p == 0 (core.py:256-257)
 
     @property
     def n_dyn(self) -> int:
@@ -39,7 +40,8 @@ class LayerDims:
         if dtype not in _TORCH_DT:
             raise TypeError(f"DCMoE supports float32 and bfloat16, got {dtype}")
         return DcmoeConfig(self.hidden_size, self.n_real, self.n_null, self.n_fix, self.dynamic_intermediate_size,
-                           self.shared_intermediate_size, _TORCH_DT[dtype], 0, float(self.top_p), float(self.jitter_eps))
+                           self.shared_intermediate_size, _TORCH_DT[dtype], int(self.fixed_top_k) if self.top_p == 0 else 0,
+                           float(self.top_p), float(self.jitter_eps))
 
 
 def _ptr(t: Optional[torch.Tensor]):
