@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
         const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
         int raw, mk;
         float gw, ga;
-        route_token<BF16, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+        // (a token past T routes a one-hot row: all-zero logits are route_token's slowest input, a nine-way tie)
+        route_token<BF16, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
         if (valid && j < E) {
             if constexpr (BF16) {
                 ((__nv_bfloat16*)logits_out)[t * E + j] = __float2bfloat16_rn(l);
@@ -525,7 +526,7 @@ router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
             const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
             int raw, mk;
             float gw, ga;
-            route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            route_token<true, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
             const long long q2 = rc.dbg ? clock64() : 0;
             if (valid && j < E) {
                 logits_out[t * E + j] = __float2bfloat16_rn(l);
@@ -785,7 +786,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
             int raw, mk;
             float gw, ga;
-            route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+            route_token<true, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
             const long long q2 = rc.dbg ? clock64() : 0;
             if (valid && j < E) {
                 logits_out[t * E + j] = __float2bfloat16_rn(l);
@@ -855,6 +856,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     const int n_dyn = NDYN ? NDYN : rc.n_dyn;
     grid_dep_wait();     // (launched programmatically dependent on whatever precedes it, e.g. dcmoe_rmsnorm)
     grid_dep_launch();   // the GEMM-1 CTAs may come up on the other SMs and run their prologue meanwhile
+    const long long t_fs0 = rc.dbg ? clock64() : 0;
     // ---- phase 1: gate projection, warp = (token block of 16, K eighth) ----
     {
         const int blk = warp >> 3, ks = warp & 7;
@@ -900,6 +902,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         }
     }
     __syncthreads();
+    if (rc.dbg && tid == 0) rc.dbg[1] = clock64() - t_fs0;   // gate projection done
     // ---- phase 2: routing, warp = 2 tokens ----
     {
         const int half = lane >> 4, j = lane & 15;
@@ -914,9 +917,15 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
             l = bf16_round(l);
         }
         const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
-        int raw, mk;
-        float gw, ga;
-        route_token<true, NDYN, NE>(l, j, half, am, rc, raw, mk, gw, ga);
+        int raw = 0, mk = 0;
+        float gw = 0.0f, ga = 0.0f;
+        // Warps without a token skip the routing; the idle half of the last warp routes a one-hot row.  (All-zero
+        // logits are the WORST case of route_token -- a nine-way tie, seven near-tie softmaxes -- and the 28 idle
+        // warps of a T = 8 call used to hold the barrier below for 9,400 cycles after the real tokens were done.)
+        if (warp * 2 < T) {
+            const float lr = valid ? l : (j == 0 ? 8.0f : 0.0f);
+            route_token<true, NDYN, NE>(lr, j, half, am, rc, raw, mk, gw, ga);
+        }
         if (valid && j < E) {
             logits_out[(int64_t)t * E + j] = __float2bfloat16_rn(l);
             gw_out[(int64_t)t * E + j] = __float2bfloat16_rn(gw);
@@ -930,14 +939,19 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         }
     }
     __syncthreads();
+    if (rc.dbg && tid == 0) rc.dbg[2] = clock64() - t_fs0;   // routing done
     // ---- phase 3: plan ----
     if (tid < n_real) {
         int c = 0;
         for (int t = 0; t < T; ++t) c += s_mask[t][tid];
         s_cnt[tid] = c;
+        if (rc.dbg && tid == 0) rc.dbg[9] = clock64() - t_fs0;
         pv.counts[tid] = c;
+        if (rc.dbg && tid == 0) rc.dbg[10] = clock64() - t_fs0;
     }
+    if (rc.dbg && tid == 64) rc.dbg[11] = clock64() - t_fs0;
     __syncthreads();
+    if (rc.dbg && tid == 0) rc.dbg[6] = clock64() - t_fs0;
     if (tid == 0) {
         const int n_sh = t_pad / kTileM;
         int row = t_pad, tile = 0, pair = 0;
@@ -966,6 +980,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         *pv.n_mtiles = tile;
         *pv.n_pairs = pair;
         *pv.overflow = 0;
+        if (rc.dbg) rc.dbg[7] = clock64() - t_fs0;
     }
     if (tid >= 32 && tid < 32 + n_dyn) {
         // aux loss, same reduction shape as router + plan kernels: fp32 partials per block of 16 tokens, then fp64
@@ -986,8 +1001,10 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         float tpe = (float)((double)ts / (double)T);
         float rp = bf16_round((float)(ps / (double)T));
         s_ga[0][jx] = tpe * rp;   // reuse as scratch (all reads of column jx are done by this thread)
+        if (rc.dbg && jx == 0) rc.dbg[8] = clock64() - t_fs0;
     }
     __syncthreads();
+    if (rc.dbg && tid == 0) rc.dbg[3] = clock64() - t_fs0;   // plan done
     if (tid == 0) {
         double acc = 0.0;
         for (int jx = 0; jx < n_dyn; ++jx) acc += (double)s_ga[0][jx];
@@ -1014,6 +1031,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         row_scale[2 * tid + 1] = (E - n_dyn) > 1 ? s_gw[tid][n_dyn + 1] : 0.0f;
     }
     __syncthreads();
+    if (rc.dbg && tid == 0) rc.dbg[4] = clock64() - t_fs0;   // permute staged / plan visible
     const int n_vec = H >> 3;   // 16-byte vectors per row
     for (int p = warp; p < T * n_real; p += 32) {
         const int t = p / n_real, e = p - t * n_real;
@@ -1034,6 +1052,10 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
                 if (c < n_vec) st_na_v4(dst + c, v[u]);
             }
         }
+    }
+    if (rc.dbg) {
+        __syncthreads();
+        if (tid == 0) rc.dbg[5] = clock64() - t_fs0;   // rows gathered
     }
 }
 
@@ -1168,6 +1190,13 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     rc.fixed_k = cfg->top_p == 0.0 ? cfg->fixed_top_k : 0;
     const dim3 grid(1), block(1024);
     cudaError_t err;
+    static unsigned long long* dbg = nullptr;
+    const bool debug = getenv("DCMOE_ROUTER_DEBUG") != nullptr;
+    if (debug) {
+        if (!dbg) cudaMalloc(&dbg, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), stream);
+        rc.dbg = dbg;
+    }
     if (rc.n_dyn == 9 && rc.E == 11)
         err = launch_kernel(front_small_kernel<9, 11>, grid, block, 0, stream, pdl_enabled(), (const __nv_bfloat16*)x,
                             (const __nv_bfloat16*)w_gate, attn_mask, (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad,
@@ -1178,6 +1207,15 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
                             (const __nv_bfloat16*)w_gate, attn_mask, (int)T, cfg->hidden_size, rc, cfg->n_real, (int)sz.t_pad,
                             (int)sz.max_mtiles, (__nv_bfloat16*)logits_out, top_k, expert_mask, (__nv_bfloat16*)global_weight, pv,
                             (__nv_bfloat16*)x_packed, slot_of, row_token, row_scale);
+    if (debug && err == cudaSuccess) {   // tuning only: synchronises
+        static int printed = 0;
+        cudaStreamSynchronize(stream);
+        unsigned long long h[16];
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        if (printed++ < 4)
+            fprintf(stderr, "front_small T=%lld: gate done@%llu routing done@%llu plan done@%llu slots visible@%llu rows gathered@%llu | counts@%llu tile table@%llu aux@%llu | loop@%llu store@%llu warp2 at barrier@%llu (cycles)\n",
+                    (long long)T, h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    }
     return check_cuda(err, "front_small_kernel launch");
 }
 
