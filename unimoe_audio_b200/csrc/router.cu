@@ -857,11 +857,15 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     grid_dep_wait();     // (launched programmatically dependent on whatever precedes it, e.g. dcmoe_rmsnorm)
     grid_dep_launch();   // the GEMM-1 CTAs may come up on the other SMs and run their prologue meanwhile
     const long long t_fs0 = rc.dbg ? clock64() : 0;
-    // ---- phase 1: gate projection, warp = (token block of 16, K eighth) ----
+    // ---- phase 1: gate projection, warp = (token block of 16, K slice) ----
+    // all 32 warps work whatever T is: K is cut 32 / 16 / 8 ways for <= 16 / 32 / 64 tokens (one round of loads per
+    // warp at T <= 16: the phase is a DRAM round trip, not arithmetic); a slice is a multiple of 32 columns
+    const int nblk2 = T <= 16 ? 1 : (T <= 32 ? 2 : 4);
+    const int ksplit = min(32 / nblk2, H >> 5);
     {
-        const int blk = warp >> 3, ks = warp & 7;
-        if (blk * kRouterBlock < T) {
-            const int Kq = H >> 3, k0 = ks * Kq;
+        const int blk = warp / ksplit, ks = warp - blk * ksplit;
+        if (blk < nblk2 && blk * kRouterBlock < T) {
+            const int Kq = H / ksplit, k0 = ks * Kq;
             const int g = lane >> 2, tq = lane & 3;
             const int r0 = blk * kRouterBlock + g, r1 = r0 + 8;
             const bool v0 = r0 < T, v1 = r1 < T;
@@ -890,7 +894,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
                     mma_bf16_16816(c1, a[u].z, b[u].z, a[u].w, b[u].w, q1[u].z, q1[u].w);
                 }
             }
-            float (*r)[16] = red[blk][ks];
+            float (*r)[16] = (&red[0][0])[blk * ksplit + ks];
             r[g][2 * tq] = c0[0];
             r[g][2 * tq + 1] = c0[1];
             r[g + 8][2 * tq] = c0[2];
@@ -911,9 +915,9 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         float l = 0.0f;
         if (valid && j < E) {
             const int blk = t >> 4, tl = t & 15;
-            l = red[blk][0][tl][j];
-#pragma unroll
-            for (int ks = 1; ks < 8; ++ks) l = __fadd_rn(l, red[blk][ks][tl][j]);
+            float (*rb)[16][16] = &red[0][0] + blk * ksplit;
+            l = rb[0][tl][j];
+            for (int ks = 1; ks < ksplit; ++ks) l = __fadd_rn(l, rb[ks][tl][j]);
             l = bf16_round(l);
         }
         const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
@@ -1033,7 +1037,9 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     __syncthreads();
     if (rc.dbg && tid == 0) rc.dbg[4] = clock64() - t_fs0;   // permute staged / plan visible
     const int n_vec = H >> 3;   // 16-byte vectors per row
-    for (int p = warp; p < T * n_real; p += 32) {
+    // (x_packed == nullptr: more than 16 tokens -- one CTA would copy the rows at ~50 GB/s, 11 us for 40 tokens; the
+    // launcher follows up with gather_rows_kernel on many CTAs instead)
+    for (int p = warp; x_packed != nullptr && p < T * n_real; p += 32) {
         const int t = p / n_real, e = p - t * n_real;
         const int slot = s_slot[t][e];
         if (slot < 0) continue;
@@ -1056,6 +1062,34 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     if (rc.dbg) {
         __syncthreads();
         if (tid == 0) rc.dbg[5] = clock64() - t_fs0;   // rows gathered
+    }
+}
+
+// row gather of the decode front end for 16 < T <= 64: one warp per (token, routed expert) pair
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ slot_of,
+                                                          int n_pairs, int n_real, int H, int t_pad,
+                                                          __nv_bfloat16* __restrict__ x_packed) {
+    grid_dep_wait();
+    grid_dep_launch();
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    const int slot = slot_of[p];
+    if (slot < 0) return;
+    const int t = p / n_real, n_vec = H >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)t * H);
+    uint4* dst = reinterpret_cast<uint4*>(x_packed + (int64_t)(slot - t_pad) * H);
+    for (int c0 = 0; c0 < n_vec; c0 += 256) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < n_vec) v[u] = ld_ca_v4(src + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            if (c < n_vec) st_na_v4(dst + c, v[u]);
+        }
     }
 }
 
@@ -1190,6 +1224,8 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     rc.fixed_k = cfg->top_p == 0.0 ? cfg->fixed_top_k : 0;
     const dim3 grid(1), block(1024);
     cudaError_t err;
+    void* const x_packed_all = x_packed;
+    if (T > 16) x_packed = nullptr;     // rows are gathered by gather_rows_kernel below
     static unsigned long long* dbg = nullptr;
     const bool debug = getenv("DCMOE_ROUTER_DEBUG") != nullptr;
     if (debug) {
@@ -1215,6 +1251,12 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
         if (printed++ < 4)
             fprintf(stderr, "front_small T=%lld: gate done@%llu routing done@%llu plan done@%llu slots visible@%llu rows gathered@%llu | counts@%llu tile table@%llu aux@%llu | loop@%llu store@%llu warp2 at barrier@%llu (cycles)\n",
                     (long long)T, h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    }
+    if (err == cudaSuccess && T > 16) {
+        const int n_pairs = (int)T * cfg->n_real;
+        err = launch_kernel(gather_rows_kernel, dim3((unsigned)ceil_div(n_pairs, 8)), dim3(256), 0, stream, pdl_enabled(),
+                            (const __nv_bfloat16*)x, (const int32_t*)slot_of, n_pairs, cfg->n_real, cfg->hidden_size,
+                            (int)sz.t_pad, (__nv_bfloat16*)x_packed_all);
     }
     return check_cuda(err, "front_small_kernel launch");
 }
