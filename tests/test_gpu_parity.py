@@ -704,3 +704,31 @@ def test_fixed_topk_layer_matches_reference_golden_and_oracle(T, dev):
         scale = float(np.abs(g["final_rows"]).max())
         err = (out[0].float().cpu().reshape(256, 2048)[::4] - torch.from_numpy(g["final_rows"])).abs()
         assert (err <= 2e-2 * scale).float().mean() > 0.995
+
+
+def test_decode_sized_kernels_random_sweep(dev):
+    """Every token count 1..64 once (random masks on a third of them, peaky and flat routers so that 1..9 weight
+    groups are hit): the decode-sized path (fused front end / gather kernel / weight-streaming GEMMs) must equal
+    the large-tile path bit for bit."""
+    dt = torch.bfloat16
+    m, W = _module(dt, dev, seed=6)
+    g = torch.Generator().manual_seed(2024)
+    groups_seen = set()
+    for T in range(1, 65):
+        scale = (0.3, 1.0, 6.0)[T % 3]          # flat -> many experts per token, peaky -> one
+        x = (torch.randn(T, 1, 2048, generator=g) * scale).to(dt).to(dev)
+        mask = (torch.rand(T, 1, generator=g) > 0.3).to(torch.int64).to(dev) if T % 3 == 0 else None
+        m.ffn_impl = 0
+        m.use_front_small = True
+        a = [t.clone() for t in m(x, mask, None)]
+        groups_seen.add(int(m.last_workspace.n_mtiles.item()))
+        m.ffn_impl = 2
+        m.use_front_small = False
+        b = m(x, mask, None, router_logits=a[1])
+        torch.cuda.synchronize()
+        m.ffn_impl = None
+        m.use_front_small = True
+        assert torch.equal(a[3], b[3]) and torch.equal(a[2], b[2]) and torch.equal(a[4], b[4]), T
+        assert torch.equal(a[0], b[0]), T
+        assert abs(a[5].item() - b[5].item()) <= 1e-6 * max(1.0, abs(b[5].item())), T
+    assert len(groups_seen) >= 5, groups_seen
