@@ -153,6 +153,23 @@ def _module(dt, dev, seed=0, ffn_impl=None):
     return m, W
 
 
+class _env:
+    """Temporarily set a process environment variable (the library reads its tuning switches with getenv per call)."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = os.environ.get(self.name)
+        os.environ[self.name] = self.value
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop(self.name, None)
+        else:
+            os.environ[self.name] = self.old
+
+
 def _check_layer(out, ref, dt):
     rtol = 1e-5 if dt == torch.float32 else 1e-2
     a, b = out.float().cpu(), ref.float()
@@ -352,9 +369,9 @@ def test_cta_pair_ffn_matches_single_cta_ffn(B, S, dev):
 @pytest.mark.parametrize("T,masked", [(1, False), (2, False), (16, False), (17, True), (32, False), (33, False), (64, True)])
 def test_decode_sized_weight_streaming_ffn_matches_large_tiles(T, masked, dev):
     """T <= 64 runs the weight-streaming tcgen05 GEMMs (ffn_tcgen05_stream.cu: 16-column granules divided evenly over
-    the SMs, 16/32/64-row A box, register-direct stores).  Same K order and fp32 accumulation as the 128x256 tiles,
-    so the layer output must equal the CTA-pair kernel's (which always uses the large tiles) bit for bit, and match
-    the oracle."""
+    the SMs, weights as the MMA M operand, register-direct stores).  With one GEMM-2 accumulator the K order and fp32
+    accumulation are those of the 128x256 tiles: the layer output equals the CTA-pair kernel's (always large tiles)
+    bit for bit.  The default (four GEMM-2 accumulators) differs by fp32 reassociation only.  Both match the oracle."""
     dt = torch.bfloat16
     m, W = _module(dt, dev, seed=4)
     g = torch.Generator().manual_seed(500 + T)
@@ -364,12 +381,18 @@ def test_decode_sized_weight_streaming_ffn_matches_large_tiles(T, masked, dev):
         mask = (torch.rand(T, 1, generator=g) > 0.3).to(torch.int64).to(dev)
     m.ffn_impl = 0
     out_small = [t.clone() for t in m(x, mask, None)]
+    with _env("DCMOE_FFN_STREAM_KSPLIT", "0"):          # GEMM-2 with one accumulator: same summation order
+        out_exact = [t.clone() for t in m(x, mask, None)]
     m.ffn_impl = 2
     out_large = m(x, mask, None)
     torch.cuda.synchronize()
     m.ffn_impl = None
     assert torch.equal(out_small[3], out_large[3])
-    assert torch.equal(out_small[0], out_large[0])
+    assert torch.equal(out_exact[0], out_large[0])
+    # default: four GEMM-2 accumulators summed in the epilogue -> fp32 reassociation only
+    a, b = out_small[0].float(), out_large[0].float()
+    assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item()
+    assert (a != b).float().mean().item() < 0.05
     ref = O.forward(x.cpu(), W, None if mask is None else mask.cpu(), logits=out_small[1].cpu())
     assert torch.equal(out_small[3].cpu(), ref.expert_mask)
     _check_layer(out_small[0].reshape(T, 2048), ref.final_hidden_states.reshape(T, 2048), dt)
@@ -471,7 +494,8 @@ def test_weight_streaming_ffn_on_a_capped_grid(max_ctas, dev):
         with pytest.raises(RuntimeError):
             ops.grouped_ffn(x.reshape(9, 2048), m._w13, m._w2, ws, 3, phase=phase_bits)
         return
-    ops.grouped_ffn(x.reshape(9, 2048), m._w13, m._w2, ws, 3, phase=phase_bits)
+    with _env("DCMOE_FFN_STREAM_KSPLIT", "0"):
+        ops.grouped_ffn(x.reshape(9, 2048), m._w13, m._w2, ws, 3, phase=phase_bits)
     torch.cuda.synchronize()
     m.ffn_impl = None
     mt = ws.mtiles[: int(ws.n_mtiles.item())].cpu()
@@ -720,7 +744,8 @@ def test_decode_sized_kernels_random_sweep(dev):
         mask = (torch.rand(T, 1, generator=g) > 0.3).to(torch.int64).to(dev) if T % 3 == 0 else None
         m.ffn_impl = 0
         m.use_front_small = True
-        a = [t.clone() for t in m(x, mask, None)]
+        with _env("DCMOE_FFN_STREAM_KSPLIT", "0"):
+            a = [t.clone() for t in m(x, mask, None)]
         groups_seen.add(int(m.last_workspace.n_mtiles.item()))
         m.ffn_impl = 2
         m.use_front_small = False

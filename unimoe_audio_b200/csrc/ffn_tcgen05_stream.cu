@@ -20,7 +20,11 @@
 //     one box per producer lane; the token box is 16 / 32 / 64 rows;
 //   * the epilogue reads TMEM lane = output column, TMEM column = token, applies SwiGLU and the routing weight
 //     (GEMM-1) and stores the valid tokens straight from registers.
-// Same K order and fp32 accumulation per output element as ffn_tcgen05.cu: h and y are bit-identical (tested).
+// Same K order and fp32 accumulation per output element as ffn_tcgen05.cu: h is bit-identical, and so is y with
+// DCMOE_FFN_STREAM_KSPLIT=0 (tested).  By default GEMM-2 spreads the four k16 steps of a stage over four accumulators
+// that are summed in the epilogue -- (a0 + a1) + (a2 + a3), a fixed order: deterministic, fp32-reassociation-level
+// differences from the large tiles -- because a single accumulator makes its K loop a dependent MMA chain
+// (GEMM-2: 26 -> 23 us).
 #include <cuda.h>
 
 #include <algorithm>
@@ -85,6 +89,7 @@ struct StreamParams {
     int stages;
     __nv_bfloat16* out; // h / y
     int ld_out;
+    int ksplit;         // GEMM-2 only: 1 = the four k16 steps of a stage go to four accumulators (summed in the epilogue)
     unsigned long long* dbg;   // tuning (DCMOE_FFN_STREAM_DEBUG=1): per-CTA cycle counters, else nullptr
 };
 
@@ -271,6 +276,18 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
                 const uint32_t w_addr = tok_addr + p.a_alloc;
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
+                    if (!SWIGLU && p.ksplit) {
+                        // MMAs into one accumulator are a ~140-cycle dependent chain each; GEMM-2 has a single M-tile
+                        // per sub-segment, so its K loop is bound by that chain.  Four accumulators (one per k16 step
+                        // of a stage), summed in the epilogue, make the steps independent.
+                        const uint32_t acc_k = (uint32_t)(kb != 0);
+                        umma_bf16(tmem_base + (uint32_t)(k * p.n_tok), make_smem_desc(w_addr) + (uint64_t)(2 * k),
+                                  tdesc + (uint64_t)(2 * k), idesc, acc_k);
+                        if (ng1 > 0)
+                            umma_bf16(tmem_base + (uint32_t)((4 + k) * p.n_tok), make_smem_desc(w_addr + nb0 * BOX_BYTES) + (uint64_t)(2 * k),
+                                      tdesc + (uint64_t)(2 * k), idesc, acc_k);
+                        continue;
+                    }
                     const uint32_t accum = (uint32_t)((kb | k) != 0);
                     // M-tiles in B-tile order: [sub 0: gate | up] [sub 1: gate | up]  (GEMM-2: [sub 0] [sub 1])
                     umma_bf16(tmem_base, make_smem_desc(w_addr) + (uint64_t)(2 * k), tdesc + (uint64_t)(2 * k), idesc, accum);
@@ -314,12 +331,24 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
             if (wq * 32 >= ngs * GR) continue;                        // (warp-uniform) no valid lane in this quarter
             const bool lane_ok = c_local < ngs * GR;
             const int col = (sg.g0 + sub * ng0) * GR + c_local;        // h / y column of this lane
-            const uint32_t t_acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((SWIGLU ? 2 : 1) * sub * p.n_tok);
+            const bool ks4 = !SWIGLU && p.ksplit;
+            const uint32_t t_acc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((SWIGLU ? 2 : (ks4 ? 4 : 1)) * sub * p.n_tok);
             const int sel = (SWIGLU && shared_grp && col >= p.split_col) ? 1 : 0;
             for (int n0 = 0; n0 < mt.rows; n0 += 16) {                // 16 tokens per TMEM load
                 uint32_t g[16], u[16];
                 tmem_ld16(t_acc + (uint32_t)n0, g);
                 if (SWIGLU) tmem_ld16(t_acc + (uint32_t)(p.n_tok + n0), u);
+                if (ks4) {   // (a0 + a1) + (a2 + a3), fixed order
+                    uint32_t a2[16], a3[16];
+                    tmem_ld16(t_acc + (uint32_t)(p.n_tok + n0), u);
+                    tmem_ld16(t_acc + (uint32_t)(2 * p.n_tok + n0), a2);
+                    tmem_ld16(t_acc + (uint32_t)(3 * p.n_tok + n0), a3);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        g[e] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(g[e]), __uint_as_float(u[e])),
+                                                         __fadd_rn(__uint_as_float(a2[e]), __uint_as_float(a3[e]))));
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
@@ -430,6 +459,11 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     p2.stages = std::min(MAX_STAGES, RING_BYTES / p2.stage_bytes);
     p2.out = static_cast<__nv_bfloat16*>(y);
     p2.ld_out = H;
+    p1.ksplit = 0;
+    {
+        const char* e = getenv("DCMOE_FFN_STREAM_KSPLIT");   // 0: one accumulator (y bit-identical to the large tiles)
+        p2.ksplit = (e && e[0] == '0') ? 0 : 1;
+    }
 
     static unsigned long long* dbg = nullptr;
     const bool debug = getenv("DCMOE_FFN_STREAM_DEBUG") != nullptr;
