@@ -206,6 +206,13 @@ int dcmoe_rmsnorm(const void* x, const void* weight, double eps, int64_t T, cons
 int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
                   void* out, void* stream);
 
+/* dcmoe_combine that also copies the layer's auxiliary loss (a float in the plan buffer, written by dcmoe_plan /
+ * dcmoe_front_small: core.py:361-389) into a caller-owned scalar inside the same launch -- the reference returns
+ * aux_loss as a fresh tensor per call (core.py:358); this saves the separate 4-byte copy kernel per layer call.
+ *   aux_src      &plan[layout.aux_loss]      aux_dst   [1] float */
+int dcmoe_combine_aux(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
+                      void* out, const float* aux_src, float* aux_dst, void* stream);
+
 /*
  * Weight packing (one-off, at load time): from the reference's separate gate_proj / up_proj / down_proj
  * matrices (state-dict keys in SURVEY.md 8b) into the grouped layouts above.

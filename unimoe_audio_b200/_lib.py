@@ -55,6 +55,8 @@ SIGNATURES = {
     "dcmoe_grouped_ffn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dcmoe_combine": (c_int, [c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p]),
+    "dcmoe_combine_aux": (c_int, [c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "dcmoe_rmsnorm": (c_int, [c_void_p, c_void_p, c_double, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p]),
     "dcmoe_pack_expert": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(DcmoeConfig), c_void_p, c_void_p,
                                   c_void_p]),

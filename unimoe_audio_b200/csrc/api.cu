@@ -146,7 +146,8 @@ int launch_front_small(const void*, const void*, const int32_t*, int64_t, const 
                        void*, int64_t*, int32_t*, void*, void*, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_permute(const void*, const int32_t*, const void*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
                    void*, int32_t*, int32_t*, float*, cudaStream_t);
-int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, const void*, void*, cudaStream_t);
+int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, const void*, void*, const float*, float*,
+                   cudaStream_t);
 int launch_pack(const void*, const void*, const void*, int, int, const dcmoe_config*, void*, void*, cudaStream_t);
 int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void* plan, dcmoe_sizes* sz, PlanView* pv);
 int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
@@ -325,7 +326,17 @@ int dcmoe_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_
                   void* out, void* stream) {
     DCMOE_PROLOGUE(T)
     if (T > 0 && (!y || !slot_of || !out)) { set_error("dcmoe_combine: NULL pointer argument"); return DCMOE_ERR_INVALID; }
-    return launch_combine(y, slot_of, T, cfg, residual, out, (cudaStream_t)stream);
+    return launch_combine(y, slot_of, T, cfg, residual, out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dcmoe_combine_aux(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
+                      void* out, const float* aux_src, float* aux_dst, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if ((T > 0 && (!y || !slot_of || !out)) || !aux_src || !aux_dst) {
+        set_error("dcmoe_combine_aux: NULL pointer argument");
+        return DCMOE_ERR_INVALID;
+    }
+    return launch_combine(y, slot_of, T, cfg, residual, out, aux_src, aux_dst, (cudaStream_t)stream);
 }
 
 int dcmoe_rmsnorm(const void* x, const void* weight, double eps, int64_t T, const dcmoe_config* cfg, void* out,

@@ -25,6 +25,8 @@ struct EpPeers {
     char* x_packed[kMaxRanks];
     float* row_scale[kMaxRanks];
     const char* y[kMaxRanks];
+    const float* aux_src;   // single-GPU combine: optional 4-byte copy of the plan's aux loss into a per-call output
+    float* aux_dst;
 };
 
 // ep_meta (device int32): [0,16) dest_base[e]  row-space row ON THE OWNER where this rank's rows of expert e start
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
     const int n_vec = H * ESIZE / 16;
     const int64_t row_bytes = (int64_t)H * ESIZE;
     grid_dep_wait();   // (decode-sized calls launch this kernel programmatically dependent on GEMM-2; else a no-op)
+    if (MODE == 0 && peers.aux_dst != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *peers.aux_dst = *peers.aux_src;
     for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < T; t += (int64_t)gridDim.x * 8) {   // grid may be capped
     // compact source list, in accumulation order: lane i < n_src holds the base pointer of source row i
     // (selected routed rows in expert order, then the shared row)
@@ -375,10 +378,15 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
 
 // single-GPU combine = the expert-parallel combine with one rank (peers.y[0] = y)
 int launch_combine(const void* y, const int32_t* slot_of, int64_t T, const dcmoe_config* cfg, const void* residual,
-                   void* out, cudaStream_t stream) {
-    if (T == 0) return DCMOE_OK;
+                   void* out, const float* aux_src, float* aux_dst, cudaStream_t stream) {
+    if (T == 0) {
+        if (aux_dst) return check_cuda(cudaMemcpyAsync(aux_dst, aux_src, 4, cudaMemcpyDeviceToDevice, stream), "aux copy");
+        return DCMOE_OK;
+    }
     EpPeers peers{};
     peers.y[0] = (const char*)y;
+    peers.aux_src = aux_src;
+    peers.aux_dst = aux_dst;
     dim3 grid((unsigned)ceil_div(T, 8)), block(256);
     const bool pdl = pdl_enabled() && T <= 64;   // decode-sized chain: come up under the tail of GEMM-2
     if (cfg->dtype == DCMOE_BF16)

@@ -280,9 +280,11 @@ class DCMoE(nn.Module):
                 res = residual.reshape(T, H)
                 if not res.is_contiguous():
                     res = res.contiguous()
-            ops.combine(ws, out, res)
+            aux = torch.empty((), dtype=torch.float32, device=x.device)
+            ops.combine(ws, out, res, aux_out=aux)      # the 4-byte aux copy rides in the combine launch
             hook("combine")
-        aux = ws.aux_loss.clone().reshape(())
+        else:
+            aux = ws.aux_loss.clone().reshape(())
         if self.mlp_dynamic_top_p == 0:
             top_k = top_k.to(torch.int32)        # the reference builds it with torch.full(..., dtype=torch.int) (core.py:257)
         return out, logits, top_k, mask, gw, aux

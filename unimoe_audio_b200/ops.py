@@ -180,10 +180,18 @@ def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Worksp
                                      impl, phase, _stream()), "dcmoe_grouped_ffn")
 
 
-def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] = None):
+def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] = None,
+            aux_out: Optional[torch.Tensor] = None):
+    """Combine (+ optional fused residual add).  With ``aux_out`` (a float32 scalar tensor) the same launch also copies
+    the plan's auxiliary loss into it, so the caller gets a per-call aux tensor without a separate copy kernel."""
     lib = _lib.load()
-    _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(residual), _ptr(out), _stream()),
-               "dcmoe_combine")
+    if aux_out is None:
+        _lib.check(lib.dcmoe_combine(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(residual), _ptr(out), _stream()),
+                   "dcmoe_combine")
+    else:
+        _lib.check(lib.dcmoe_combine_aux(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(residual), _ptr(out),
+                                         ws.plan.data_ptr() + ws.layout.aux_loss, _ptr(aux_out), _stream()),
+                   "dcmoe_combine_aux")
 
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, out: Optional[torch.Tensor] = None):
