@@ -42,6 +42,35 @@ def main():
     torch.cuda.synchronize()
     ok = torch.equal(out[0][0], ref[0][0, off:off + T_loc[rank]]) and torch.equal(out[3], ref[3][off:off + T_loc[rank]])
     err = (out[0][0].float() - ref[0][0, off:off + T_loc[rank]].float()).abs().max().item()
+    # the reference's own way to ask for expert parallelism: config.ep_size (core.py:505-520) -- the module then
+    # holds only this rank's routed experts and DCMoE.forward runs the expert-parallel path by itself
+    n_loc = 8 // world
+    with torch.device("meta"):
+        m2 = DCMoE(dict(cfg, ep_size=world))
+    m2 = m2.to(dt).to_empty(device=dev).eval()
+    sd = m.state_dict()
+    pre = "dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts."
+    local = {k: v for k, v in sd.items() if not k.startswith(pre)}
+    for l in range(n_loc):
+        for proj in ("gate_proj", "up_proj", "down_proj"):
+            local[f"{pre}{l}.{proj}.weight"] = sd[f"{pre}{rank * n_loc + l}.{proj}.weight"]
+    m2.load_state_dict(local)
+    assert len(m2.dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts) == n_loc
+    out2 = m2(x_mine, None, None)
+    torch.cuda.synchronize()
+    ok2 = all(torch.equal(a, b) for a, b in zip(out2, out))
+    # avg_hidden_states_last (core.py:355-356): all-reduce AVG of the final hidden states over the group
+    x_eq = x_all[:, rank * 256:(rank + 1) * 256].contiguous()
+    base = m2(x_eq, None, None)[0].clone()
+    dist.all_reduce(base)
+    base.div_(world)
+    m2.avg_hidden_states_last = True
+    out3 = m2(x_eq, None, None)
+    m2.avg_hidden_states_last = False
+    torch.cuda.synchronize()
+    ok3 = torch.equal(out3[0], base)
+    print(f"rank {rank}: ep_size-configured module equal={ok2} avg_hidden_states_last equal={ok3}", flush=True)
+    ok = ok and ok2 and ok3
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"rank {rank}: equal={ok} max_abs_err={err:.3e}", flush=True)

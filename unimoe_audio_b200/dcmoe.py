@@ -129,8 +129,9 @@ class DCMoE(nn.Module):
             raise ValueError("mlp_dynamic_top_p == 0 (fixed top-k routing, core.py:256-257) needs mlp_dynamic_top_k >= 1")
         if self.token_drop:
             raise NotImplementedError("token_drop=True (core.py:302-329) is not implemented; utils/config.json sets it False")
-        if self.avg_hidden_states_last:
-            raise NotImplementedError("avg_hidden_states_last=True (core.py:355-356) is not implemented")
+        if self.avg_hidden_states_last and self.ep_size == 1:
+            raise NotImplementedError("avg_hidden_states_last=True (core.py:355-356) averages over the expert-parallel "
+                                      "group and needs ep_size > 1")
         if g("hidden_act", "silu") != "silu":
             raise NotImplementedError("only hidden_act='silu' (utils/config.json) is implemented")
         self.dims = LayerDims(
@@ -154,6 +155,7 @@ class DCMoE(nn.Module):
         self.last_workspace: Optional[Workspace] = None
         self.stage_hook = None            # optional callable(stage_name) invoked between kernel launches (bench)
         self._reference_released = False
+        self._ep = None                   # ExpertParallelDCMoE, built on the first forward when ep_size > 1
         self.use_front_small = True       # T <= 64 (bf16): fused router + plan + permute launch
 
     # ------------------------------------------------------------------ weights
@@ -237,7 +239,23 @@ class DCMoE(nn.Module):
         if dt != self.gate.weight.dtype:
             raise TypeError(f"hidden_states dtype {dt} != parameter dtype {self.gate.weight.dtype}")
         if self.ep_size != 1:
-            raise NotImplementedError("ep_size > 1: use unimoe_audio_b200.ep.ExpertParallelDCMoE")
+            # expert parallelism configured the reference's way (config.ep_size, core.py:505-520): this rank holds
+            # num_experts / ep_size routed experts and the forward runs ep.ExpertParallelDCMoE over the group set by
+            # deepspeed_moe._set_ep_group (default: the world group)
+            if router_logits is not None or residual is not None:
+                raise NotImplementedError("router_logits / residual are single-GPU extras")
+            if self._ep is None:
+                import torch.distributed as dist
+
+                from .ep import ExpertParallelDCMoE
+                if not dist.is_initialized():
+                    raise RuntimeError("ep_size > 1 needs an initialised torch.distributed process group (NCCL)")
+                group = self.dynamic_real_moe.deepspeed_moe.ep_group or dist.group.WORLD
+                if dist.get_world_size(group) != self.ep_size:
+                    raise ValueError(f"ep_size ({self.ep_size}) != size of the expert-parallel group "
+                                     f"({dist.get_world_size(group)})")
+                self._ep = ExpertParallelDCMoE(self, group)
+            return self._ep(hidden_states, attention_mask, None)
         B, S, H = hidden_states.shape
         T = B * S
         x = hidden_states.reshape(T, H)

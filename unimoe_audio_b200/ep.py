@@ -350,6 +350,10 @@ class ExpertParallelDCMoE:
             hook("wait_combine")
             self.phase_combine(out.view(T, H), 2)
             hook("ep_combine_final")
+        if getattr(self.m, "avg_hidden_states_last", False):
+            # core.py:355-356: all_reduce(final_hidden_states, AVG) over the expert-parallel group in eval mode
+            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+            out.div_(self.world)
         logits, top_k, mask, gw = self._route
         return out, logits, top_k, mask, gw, self._aux
 
