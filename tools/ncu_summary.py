@@ -20,6 +20,7 @@ def main():
            "(BASELINE.json configs[1]: 8 x 2048 tokens, bf16).\n"]
     for f, note in (("profiles/r01_ffn_gemm.ncu-rep", "grouped FFN GEMMs"),
                     ("profiles/r01_router_plan_permute_combine.ncu-rep", "router / plan / permute / combine"),
+                    ("profiles/r01_router_final.ncu-rep", "router, final version of the round (29 warps, three routing groups)"),
                     ("profiles/r01_decode_T8.ncu-rep", "decode-sized call, T = 8 (tools/decode_once.py): fused front end, "
                                                        "weight-streaming GEMM-1 / GEMM-2, combine")):
         txt = subprocess.run(["ncu", "-i", os.path.join(ROOT, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
