@@ -1,4 +1,4 @@
-"""Decode-sized GEMM-1 / GEMM-2 device time for one ring geometry (DCMOE_FFN_GEOM / DCMOE_FFN_SMALL), with the
+"""Decode-sized GEMM-1 / GEMM-2 device time (DCMOE_FFN_STREAM=0: the 128x256-tile kernel instead of the weight-streaming one), with the
 weights of three layers rotated so that nothing is served from L2.
     python tools/bench_decode_gemm.py [T ...]"""
 import os
@@ -56,7 +56,7 @@ def main():
                 best = min(best, s.elapsed_time(e) / reps * 1e3)
             res[phase] = best
         hit_mb = n_groups * 3 * 2048 * 2752 * 2 / 1e6
-        print(f"GEOM stream={os.environ.get('DCMOE_FFN_STREAM', '1')} T={T:3d} "
+        print(f"stream={os.environ.get('DCMOE_FFN_STREAM', '1')} T={T:3d} "
               f"groups={n_groups}  gemm1 {res[1]:6.1f} us  gemm2 {res[2]:6.1f} us  sum {res[1] + res[2]:6.1f} us "
               f"(hit weights {hit_mb:.0f} MB -> {hit_mb / 6.5297:.1f} us at 6.53 TB/s)")
 
