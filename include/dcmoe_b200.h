@@ -177,6 +177,9 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism
  *                runs the shared experts while the dispatch is still in flight.  Bits 8-19: cap on the number of
  *                persistent CTAs (0 = one per SM), to leave SMs to concurrently running dispatch / combine kernels.
+ *                Bits 21-24 / 25-27 (impl 3): expert-parallel decode -- n_loc and rank: the plan and x_packed cover all
+ *                experts (replicated routing of the gathered tokens), w13 / w2 hold this rank's n_loc routed experts as
+ *                groups 0..n_loc-1 plus the shared pair as group n_loc; only those row tiles are computed.
  *                Bit 20: never select the decode-sized kernels automatically (set by expert parallelism, where a
  *                rank can own more rows than it has tokens)
  */

@@ -93,3 +93,34 @@ def test_multi_gpu_ep_if_available(setup):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "EP_CHECK_OK" in res.stdout
+
+
+@pytest.mark.parametrize("world,T,masked", [(2, 1, False), (2, 8, True), (4, 2, False), (4, 16, False), (8, 1, False),
+                                            (8, 8, True), (8, 5, False)])
+def test_decode_sized_expert_parallel_path_matches_single_gpu(setup, world, T, masked):
+    """world * T <= 64: replicated routing of the gathered tokens, every virtual rank streams only its experts' weights
+    (+ the shared pair), the combine gathers the routed rows from the owners' y.  Same kernels and row space as a
+    single-GPU call on the gathered tokens -> every rank's slice of the 6-tuple is bit-equal to it."""
+    from unimoe_audio_b200.ep import LocalRanks
+    m, W, dev, dt = setup
+    gen = torch.Generator().manual_seed(100 * world + T)
+    xs = [(torch.randn(1, T, 2048, generator=gen) * (0.5 + r % 3)).to(dt).to(dev) for r in range(world)]
+    ams = [(torch.rand(1, T, generator=gen) > 0.3).to(torch.int64).to(dev) for _ in range(world)] if masked else None
+    lr = LocalRanks(m, world)
+    assert lr.ranks[0].decode_applicable(T, dt)
+    outs = lr.decode_forward(xs, ams)
+    torch.cuda.synchronize()
+    x_all = torch.cat(xs, dim=1)
+    am_all = None if ams is None else torch.cat(ams, dim=1)
+    ref = m(x_all, am_all, None)
+    torch.cuda.synchronize()
+    for r in range(world):
+        o, sl = outs[r], slice(r * T, (r + 1) * T)
+        for i in (1, 2, 3, 4):
+            assert torch.equal(o[i], ref[i][sl]), (r, i)
+        assert torch.equal(o[0][0], ref[0][0, sl]), f"rank {r} output differs"
+        assert torch.equal(o[5], ref[5])
+    # every rank only wrote the y rows of its own experts and of the shared pair
+    ws0 = lr.ranks[0]._dws
+    mt = ws0.mtiles[: int(ws0.n_mtiles.item())].cpu().tolist()
+    assert {g for _a, _o, g, _n in mt} >= {8}

@@ -70,7 +70,20 @@ def main():
     torch.cuda.synchronize()
     ok3 = torch.equal(out3[0], base)
     print(f"rank {rank}: ep_size-configured module equal={ok2} avg_hidden_states_last equal={ok3}", flush=True)
-    ok = ok and ok2 and ok3
+    # decode-sized calls take the replicated-routing path (ExpertParallelDCMoE.decode_forward): bit-equal to one GPU
+    ok4 = True
+    for Td in (1, 4):
+        xd_all = x_all[:, 5000 - Td * world:5000] if x_all.shape[1] >= 5000 else x_all[:, :Td * world]
+        xd = xd_all[:, rank * Td:(rank + 1) * Td].contiguous()
+        assert ep.decode_applicable(Td, dt)
+        for _ in range(3):
+            od = ep(xd, None, None)
+        torch.cuda.synchronize()
+        rd = m(xd_all.contiguous(), None, None)
+        torch.cuda.synchronize()
+        ok4 = ok4 and torch.equal(od[0][0], rd[0][0, rank * Td:(rank + 1) * Td]) and torch.equal(od[3], rd[3][rank * Td:(rank + 1) * Td])
+    print(f"rank {rank}: decode-sized expert-parallel path equal={ok4}", flush=True)
+    ok = ok and ok2 and ok3 and ok4
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"rank {rank}: equal={ok} max_abs_err={err:.3e}", flush=True)

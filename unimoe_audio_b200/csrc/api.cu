@@ -155,9 +155,9 @@ int launch_ffn_simt(const void*, const void*, const void*, const void*, const fl
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                        const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 int launch_rmsnorm(const void*, const void*, double, int64_t, const dcmoe_config*, void*, cudaStream_t);
-bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int);
+bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int, int);
 int launch_ffn_tcgen05_stream(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
-                              const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
+                              const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, int, cudaStream_t);
 int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                             const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 
@@ -284,6 +284,8 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     // 1 shared-expert tiles only, 2 routed tiles only)
     const int group_sel = (phase >> 4) & 3;
     const int max_ctas = (phase >> 8) & 0xfff;   // bits 8-19: cap on the persistent grid (0 = one CTA per SM)
+    const int ep_n_loc = (phase >> 21) & 15;     // bits 21-24 / 25-27 (impl 3 only): expert-parallel decode -- the plan covers
+    const int ep_rank = (phase >> 25) & 7;       // all experts, w13 / w2 hold this rank's ep_n_loc routed experts + the shared pair
     const bool no_decode = (phase >> 20) & 1;    // bit 20: never pick the decode kernels (expert parallelism: a rank
                                                  // can own more rows than it has tokens)
     phase &= 15;
@@ -299,12 +301,13 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     // impl 3 asks for them explicitly; impl 0 picks them unless the caller vetoes (bit 20), selects tile groups, or
     // DCMOE_FFN_STREAM=0 (A/B measurements)
     if (impl == 3) return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
-                                                    phase, max_ctas, (cudaStream_t)stream);
-    if (impl == 0 && !no_decode && group_sel == 0 && ffn_stream_applicable(T, cfg, sz, max_ctas)) {
+                                                    phase, max_ctas, ep_n_loc, ep_rank, (cudaStream_t)stream);
+    if (ep_n_loc != 0) { set_error("dcmoe_grouped_ffn: expert-parallel decode bits need impl 3"); return DCMOE_ERR_INVALID; }
+    if (impl == 0 && !no_decode && group_sel == 0 && ffn_stream_applicable(T, cfg, sz, max_ctas, 0)) {
         const char* e = getenv("DCMOE_FFN_STREAM");
         if (!(e && e[0] == '0'))
             return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase,
-                                             max_ctas, (cudaStream_t)stream);
+                                             max_ctas, 0, 0, (cudaStream_t)stream);
     }
     if (impl == 2) {
         if (cfg->dtype != DCMOE_BF16) { set_error("tcgen05 FFN is bf16 only"); return DCMOE_ERR_INVALID; }

@@ -89,6 +89,8 @@ struct StreamParams {
     int stages;
     __nv_bfloat16* out; // h / y
     int ld_out;
+    int ep_n_loc;       // expert-parallel decode: this rank owns routed experts [ep_base, ep_base + ep_n_loc) and packs
+    int ep_base;        // them as weight groups 0..ep_n_loc-1 (+ the shared pair as group ep_n_loc); 0 = all groups local
     int ksplit;         // GEMM-2 only: 1 = the four k16 steps of a stage go to four accumulators (summed in the epilogue)
     unsigned long long* dbg;   // tuning (DCMOE_FFN_STREAM_DEBUG=1): per-CTA cycle counters, else nullptr
 };
@@ -167,7 +169,22 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
     grid_dep_wait();
     grid_dep_launch();
     const long long t_start = p.dbg ? clock64() : 0;
-    const Segment sg = cta_segment(*p.n_mtiles, p.gpg);
+    // m-tiles this launch works on: all of them, or (expert-parallel decode: the plan is replicated on every rank) the
+    // ones whose weights this rank holds -- its routed experts and the shared pair
+    __shared__ int s_local_m[kMaxDyn + 1];
+    __shared__ int s_n_local;
+    if (threadIdx.x == 0) {
+        const int n_m = min(*p.n_mtiles, kMaxDyn + 1);
+        int k = 0;
+        for (int m = 0; m < n_m; ++m) {
+            const int g = p.mtiles[m].group;
+            if (p.ep_n_loc == 0 || g == p.n_real || (g >= p.ep_base && g < p.ep_base + p.ep_n_loc)) s_local_m[k++] = m;
+        }
+        s_n_local = k;
+    }
+    __syncthreads();
+    Segment sg = cta_segment(s_n_local, p.gpg);
+    if (sg.ng > 0) sg.m = s_local_m[sg.m];
     // The WEIGHTS are the MMA's M operand (128 rows = 8 granules per M-tile) and the token rows its N operand
     // (N = the A box: 16 / 32 / 64 tokens): D[weight row, token].  Nothing of the tensor-core work or of its shared
     // memory reads is padding, and an M-tile that is only partly loaded just computes lanes nobody reads.
@@ -204,7 +221,8 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
                     nrows -= sz;
                 }
             };
-            const int wbase = mt.group * p.w_rows;
+            const int wgrp = p.ep_n_loc == 0 ? mt.group : (mt.group == p.n_real ? p.ep_n_loc : mt.group - p.ep_base);
+            const int wbase = wgrp * p.w_rows;
             int dst = 0;
             for (int sub = 0; sub < 2; ++sub) {
                 const int gs = sg.g0 + sub * ng0, ngs = sub ? ng1 : ng0;
@@ -385,7 +403,7 @@ int sm_count() {
 
 }  // namespace
 
-bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, int max_ctas) {
+bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, int max_ctas, int ep_n_loc) {
     // every m-tile must be a whole weight group with at most 64 rows: T <= 64 (one shared tile, one tile per hit
     // expert), and the widest segment a CTA can get must fit the two accumulators / 32 producer lanes
     if (!(cfg->dtype == DCMOE_BF16 && T > 0 && T <= 64 && sz.t_pad == BM && cfg->dynamic_intermediate_size % GR == 0 &&
@@ -393,7 +411,7 @@ bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes
         return false;
     int n_ctas = sm_count();
     if (max_ctas > 0 && max_ctas < n_ctas) n_ctas = max_ctas;
-    const int G = cfg->n_real + 1;
+    const int G = (ep_n_loc > 0 ? ep_n_loc : cfg->n_real) + 1;   // most weight groups one launch can work on
     if (n_ctas < G) return false;
     const int per_group = n_ctas / G;
     return ceil_div(cfg->dynamic_intermediate_size / GR, per_group) <= 16 && ceil_div(cfg->hidden_size / GR, per_group) <= 16;
@@ -401,13 +419,17 @@ bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes
 
 int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                               int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv,
-                              void* h, void* y, int phase, int max_ctas, cudaStream_t stream) {
-    if (!ffn_stream_applicable(T, cfg, sz, max_ctas)) {
+                              void* h, void* y, int phase, int max_ctas, int ep_n_loc, int ep_rank, cudaStream_t stream) {
+    if (ep_n_loc < 0 || (ep_n_loc > 0 && (cfg->n_real % ep_n_loc != 0 || ep_rank < 0 || ep_rank >= cfg->n_real / ep_n_loc))) {
+        set_error("weight-streaming FFN: bad expert-parallel layout (%d local experts, rank %d)", ep_n_loc, ep_rank);
+        return DCMOE_ERR_INVALID;
+    }
+    if (!ffn_stream_applicable(T, cfg, sz, max_ctas, ep_n_loc)) {
         set_error("weight-streaming FFN needs bf16, 1 <= T <= 64 and enough CTAs per weight group (got T = %lld)", (long long)T);
         return DCMOE_ERR_INVALID;
     }
     const int H = cfg->hidden_size, Id = cfg->dynamic_intermediate_size;
-    const int G = cfg->n_real + 1;
+    const int G = (ep_n_loc > 0 ? ep_n_loc : cfg->n_real) + 1;   // weight groups in the packs handed in
     static bool attr_set = false;
     if (!attr_set) {
         int rc = check_cuda(cudaFuncSetAttribute(ffn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
@@ -460,6 +482,8 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     p2.out = static_cast<__nv_bfloat16*>(y);
     p2.ld_out = H;
     p1.ksplit = 0;
+    p1.ep_n_loc = p2.ep_n_loc = ep_n_loc;
+    p1.ep_base = p2.ep_base = ep_rank * ep_n_loc;
     {
         const char* e = getenv("DCMOE_FFN_STREAM_KSPLIT");   // 0: one accumulator (y bit-identical to the large tiles)
         p2.ksplit = (e && e[0] == '0') ? 0 : 1;

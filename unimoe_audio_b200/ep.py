@@ -134,6 +134,12 @@ class ExpertParallelDCMoE:
         self.comm_events = []        # (name, start, end) CUDA events of the comm-stream kernels, filled when a stage hook is set
         self._local_cfg = None
         self._partial = None
+        # decode-sized calls (world * T <= 64 tokens, the same T on every rank): replicated routing of the gathered tokens,
+        # local experts' rows computed by the weight-streaming kernels, combine over peer memory (see decode_forward)
+        self.decode_mode = os.environ.get("DCMOE_EP_DECODE", "1") != "0"
+        self._dws: Optional[EpWorkspace] = None
+        self._dpeer = None
+        self._dflag = None
 
     # ------------------------------------------------------------------ setup
     def pack_local_weights(self):
@@ -271,6 +277,94 @@ class ExpertParallelDCMoE:
                                         None if out is None else out.data_ptr(), max_ctas,
                                         torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
 
+    # ------------------------------------------------------------------ decode-sized calls
+    def decode_applicable(self, T: int, dtype) -> bool:
+        return (self.decode_mode and dtype == torch.bfloat16 and 0 < T * self.world <= 64 and self.m.use_front_small
+                and self.m.ffn_impl in (None, 0, 3))
+
+    def ensure_decode_workspace(self, T_total: int, device, ipc: bool) -> EpWorkspace:
+        if self._dws is None or self._dws.T != T_total:
+            self._dws = EpWorkspace(self.m.dims, torch.bfloat16, T_total, device, 0, ipc)     # worst-case rows for T_total tokens
+            self._dws.x_all = torch.empty((T_total, self.m.dims.hidden_size), dtype=torch.bfloat16, device=device)
+            self._dpeer = None
+        return self._dws
+
+    def set_decode_peers(self, y: List[int]):
+        self._dpeer = (ctypes.c_void_p * len(y))(*y)
+
+    def _exchange_decode_handles(self):
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        mine = self._dws.export_handles()
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        ys = []
+        for r in range(self.world):
+            if r == self.rank:
+                ys.append(self._dws._raw["y"][0])
+            else:
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r]["y"])
+                _lib.check(lib.dcmoe_ipc_import(buf, ctypes.byref(p)), "dcmoe_ipc_import")
+                self._imported.append(p.value)
+                ys.append(p.value)
+        self.set_decode_peers(ys)
+        self._dflag = torch.zeros(1, dtype=torch.int32, device=self._dws.device)
+
+    def decode_route_and_ffn(self, attention_mask_all=None):
+        """Replicated part of a decode-sized call, after x_all holds every rank's tokens (rank-major): fused front end
+        on all tokens (identical plan and row space on every rank), then the weight-streaming GEMMs over the row tiles
+        whose weights this rank holds (its routed experts + the shared pair)."""
+        lib = _lib.load()
+        ws = self._dws
+        self._droute = ops.front_small(ws.x_all, self.m.gate.weight.detach(), ws, attention_mask=attention_mask_all)
+        _lib.check(lib.dcmoe_grouped_ffn(ws.x_all.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(), self._w2.data_ptr(),
+                                         ws.row_scale.data_ptr(), ws.T, ws.row_capacity, ws.cfg, ws.plan.data_ptr(),
+                                         ws.h.data_ptr(), ws.y.data_ptr(), 3, (self.n_loc << 21) | (self.rank << 25),
+                                         torch.cuda.current_stream().cuda_stream), "dcmoe_grouped_ffn")
+
+    def decode_combine(self, T: int, out: torch.Tensor):
+        """Own tokens [rank * T, (rank + 1) * T): routed rows from the owners' y (peer loads), shared row from the local y."""
+        lib = _lib.load()
+        ws, d = self._dws, self.m.dims
+        es = 2
+        off = self.rank * T
+        _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr() + off * d.hidden_size * es, self._dpeer,
+                                        ws.slot_of.data_ptr() + off * d.n_real * 4, T, ws.cfg, self.world, 0, None,
+                                        out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
+
+    def decode_forward(self, hidden_states: torch.Tensor, attention_mask=None):
+        """Expert parallelism for decode-sized calls.  The dispatch / combine exchange of the large-T path costs eleven
+        launches and three collectives (340 us per layer at T = 2); with a handful of tokens it is cheaper to replicate
+        the tokens (one all-gather of world * T rows) and the routing, let every rank stream only ITS experts' weights,
+        and gather the routed rows in the combine.  Same kernels and row space as a single-GPU call on the gathered
+        tokens, so the output equals that call's bit for bit.  (aux_loss is then the loss over the gathered tokens.)"""
+        import torch.distributed as dist
+
+        B, S, H = hidden_states.shape
+        T = B * S
+        x = hidden_states.reshape(T, H)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        self.pack_local_weights()
+        ws = self.ensure_decode_workspace(T * self.world, x.device, ipc=True)
+        if self._dpeer is None:
+            self._exchange_decode_handles()
+        dist.all_gather_into_tensor(ws.x_all, x, group=self.group)     # also: every rank is done reading the previous y
+        am_all = None
+        if attention_mask is not None:
+            am = attention_mask.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+            am_all = torch.empty(T * self.world, dtype=torch.int32, device=x.device)
+            dist.all_gather_into_tensor(am_all, am, group=self.group)
+        self.decode_route_and_ffn(am_all)
+        dist.all_reduce(self._dflag, group=self.group)                 # every owner's y rows are complete
+        out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
+        self.decode_combine(T, out)
+        logits, top_k, mask, gw = (t[self.rank * T:(self.rank + 1) * T] for t in self._droute)
+        self.m.last_workspace = ws
+        return out, logits, top_k, mask, gw, ws.aux_loss.clone().reshape(())
+
     # ------------------------------------------------------------------ distributed forward
     @torch.no_grad()
     def __call__(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
@@ -280,6 +374,12 @@ class ExpertParallelDCMoE:
             raise NotImplementedError("aux_balance_weight is training-only")
         B, S, H = hidden_states.shape
         T = B * S
+        if router_logits is None and self.m.stage_hook is None and self.decode_applicable(T, hidden_states.dtype):
+            out = self.decode_forward(hidden_states, attention_mask)
+            if getattr(self.m, "avg_hidden_states_last", False):
+                dist.all_reduce(out[0], op=dist.ReduceOp.SUM, group=self.group)
+                out[0].div_(self.world)
+            return out
         x = hidden_states.reshape(T, H)
         if not x.is_contiguous():
             x = x.contiguous()
@@ -366,6 +466,30 @@ class LocalRanks:
         self.world = world
         self.split = split
         self.ranks = [ExpertParallelDCMoE(module, group=None, rank=r, world=world) for r in range(world)]
+
+    @torch.no_grad()
+    def decode_forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
+        """The decode-sized expert-parallel path (ExpertParallelDCMoE.decode_forward) with the all-gather replaced by
+        a torch.cat and the peers' y buffers by the virtual ranks' own.  Every x must have the same token count."""
+        flat = [x.reshape(-1, x.shape[-1]).contiguous() for x in xs]
+        T = flat[0].shape[0]
+        assert all(f.shape[0] == T for f in flat)
+        x_all = torch.cat(flat)
+        am_all = None if attention_masks is None else torch.cat([a.reshape(-1).to(torch.int32) for a in attention_masks])
+        for ep in self.ranks:
+            ep.pack_local_weights()
+            ws = ep.ensure_decode_workspace(T * self.world, x_all.device, ipc=False)
+            ws.x_all.copy_(x_all)
+        for ep in self.ranks:
+            ep.set_decode_peers([q._dws.y.data_ptr() for q in self.ranks])
+            ep.decode_route_and_ffn(am_all)
+        outs = []
+        for r, ep in enumerate(self.ranks):
+            out = torch.empty_like(flat[r])
+            ep.decode_combine(T, out)
+            logits, top_k, mask, gw = (t[r * T:(r + 1) * T] for t in ep._droute)
+            outs.append((out.view(xs[r].shape), logits, top_k, mask, gw, ep._dws.aux_loss.clone().reshape(())))
+        return outs
 
     @torch.no_grad()
     def forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
