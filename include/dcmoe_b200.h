@@ -187,6 +187,28 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
                       int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const void* plan, void* h, void* y,
                       int impl, int phase, void* stream);
 
+/* Device buffers of one forward, sized by dcmoe_query_sizes (all caller-owned; reused from call to call). */
+typedef struct dcmoe_workspace {
+    void* plan;        /* sizes.plan_bytes */
+    void* x_packed;    /* [row_capacity - t_pad, H] D */
+    int32_t* slot_of;  /* [T, n_real] */
+    int32_t* row_token;/* [row_capacity] */
+    float* row_scale;  /* [row_capacity, 2] (zero-initialised once) */
+    void* h;           /* [row_capacity, I_d] D */
+    void* y;           /* [row_capacity, H] D */
+} dcmoe_workspace;
+
+/*
+ * One layer forward in one host call: UniMoEAudioSparseMoeBlock.forward (core.py:236-358) = router (or the fused front
+ * end for T <= 64 in bf16) -> plan -> permute -> grouped FFN -> combine, launched back to back on `stream`; nothing is
+ * read back.  Arguments as in the per-stage calls; `residual` and `aux_out` may be NULL (aux_out: the aux loss as a
+ * per-call scalar, see dcmoe_combine_aux); impl as in dcmoe_grouped_ffn (0 for bf16, 1 for fp32).
+ */
+int dcmoe_forward(const void* x, const void* w_gate, const int32_t* attn_mask, const void* w13, const void* w2, int64_t T,
+                  int64_t row_capacity, const dcmoe_config* cfg, const dcmoe_workspace* ws, const void* residual, void* out,
+                  void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight, float* aux_out, int impl,
+                  void* stream);
+
 /*
  * Pre-MoE RMSNorm (decoder-layer glue in front of the block).  Replaces utils/UniMoE_Audio_model.py:240
  * `hidden_states = self.post_attention_layernorm(hidden_states)` (Qwen2RMSNorm, model.py:207, eps = rms_norm_eps):

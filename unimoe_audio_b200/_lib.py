@@ -24,6 +24,11 @@ class DcmoeConfig(Structure):
     ]
 
 
+class DcmoeWorkspace(Structure):
+    _fields_ = [("plan", c_void_p), ("x_packed", c_void_p), ("slot_of", c_void_p), ("row_token", c_void_p),
+                ("row_scale", c_void_p), ("h", c_void_p), ("y", c_void_p)]
+
+
 class DcmoeSizes(Structure):
     _fields_ = [("n_blocks", c_int64), ("t_pad", c_int64), ("max_mtiles", c_int64), ("row_capacity", c_int64),
                 ("plan_bytes", c_int64)]
@@ -57,6 +62,8 @@ SIGNATURES = {
     "dcmoe_combine": (c_int, [c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p]),
     "dcmoe_combine_aux": (c_int, [c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p]),
+    "dcmoe_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dcmoe_rmsnorm": (c_int, [c_void_p, c_void_p, c_double, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p]),
     "dcmoe_pack_expert": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(DcmoeConfig), c_void_p, c_void_p,
                                   c_void_p]),

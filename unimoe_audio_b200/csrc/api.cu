@@ -342,6 +342,37 @@ int dcmoe_combine_aux(const void* y, const int32_t* slot_of, int64_t T, const dc
     return launch_combine(y, slot_of, T, cfg, residual, out, aux_src, aux_dst, (cudaStream_t)stream);
 }
 
+int dcmoe_forward(const void* x, const void* w_gate, const int32_t* attn_mask, const void* w13, const void* w2, int64_t T,
+                  int64_t row_capacity, const dcmoe_config* cfg, const dcmoe_workspace* ws, const void* residual, void* out,
+                  void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight, float* aux_out, int impl,
+                  void* stream) {
+    // the calls below validate their own arguments; this entry point only sequences them (one host call per layer)
+    if (!ws) { set_error("dcmoe_forward: NULL workspace"); return DCMOE_ERR_INVALID; }
+    int rc;
+    const bool small = cfg && cfg->dtype == DCMOE_BF16 && T > 0 && T <= 64;
+    if (small) {
+        if ((rc = dcmoe_front_small(x, w_gate, attn_mask, T, row_capacity, cfg, logits_out, top_k, expert_mask, global_weight,
+                                    ws->plan, ws->x_packed, ws->slot_of, ws->row_token, ws->row_scale, stream)))
+            return rc;
+    } else {
+        if ((rc = dcmoe_router(x, w_gate, nullptr, attn_mask, T, cfg, logits_out, top_k, expert_mask, global_weight, ws->plan,
+                               stream)))
+            return rc;
+        if ((rc = dcmoe_plan(T, row_capacity, cfg, ws->plan, stream))) return rc;
+        if (T > 0 && (rc = dcmoe_permute(x, expert_mask, global_weight, T, row_capacity, cfg, ws->plan, ws->x_packed,
+                                         ws->slot_of, ws->row_token, ws->row_scale, stream)))
+            return rc;
+    }
+    if (T > 0 && (rc = dcmoe_grouped_ffn(x, ws->x_packed, w13, w2, ws->row_scale, T, row_capacity, cfg, ws->plan, ws->h, ws->y,
+                                         impl, 0, stream)))
+        return rc;
+    dcmoe_sizes sz; dcmoe_plan_layout lay;
+    if ((rc = dcmoe_query_sizes(cfg, T, row_capacity, &sz, &lay))) return rc;
+    const float* aux_src = reinterpret_cast<const float*>(static_cast<const char*>(ws->plan) + lay.aux_loss);
+    if (aux_out) return dcmoe_combine_aux(ws->y, ws->slot_of, T, cfg, residual, out, aux_src, aux_out, stream);
+    return dcmoe_combine(ws->y, ws->slot_of, T, cfg, residual, out, stream);
+}
+
 int dcmoe_rmsnorm(const void* x, const void* weight, double eps, int64_t T, const dcmoe_config* cfg, void* out,
                   void* stream) {
     DCMOE_PROLOGUE(T)

@@ -269,6 +269,20 @@ class DCMoE(nn.Module):
             wg = wg.contiguous()
         hook = self.stage_hook or (lambda _name: None)
         out = torch.empty((B, S, H), dtype=dt, device=x.device)
+        if self.stage_hook is None and router_logits is None and T > 0 and (self.use_front_small or T > 64 or dt != torch.bfloat16):
+            # the common case: the whole layer in one host call (dcmoe_forward) -- same launches as below
+            res = None
+            if residual is not None:
+                if residual.shape != hidden_states.shape or residual.dtype != dt:
+                    raise ValueError("residual must match hidden_states in shape and dtype")
+                res = residual.reshape(T, H)
+                if not res.is_contiguous():
+                    res = res.contiguous()
+            impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
+            logits, top_k, mask, gw, aux = ops.forward(x, wg, self._w13, self._w2, ws, out, attention_mask, res, impl)
+            if self.mlp_dynamic_top_p == 0:
+                top_k = top_k.to(torch.int32)
+            return out, logits, top_k, mask, gw, aux
         hook("start")
         small = (dt == torch.bfloat16 and 0 < T <= 64 and router_logits is None and self.use_front_small)
         if small:     # decode-sized call: router + plan + permute in one single-CTA launch

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import DcmoeConfig, DcmoePlanLayout, DcmoeSizes
+from ._lib import DcmoeConfig, DcmoePlanLayout, DcmoeSizes, DcmoeWorkspace
 
 _TORCH_DT = {torch.float32: _lib.DCMOE_F32, torch.bfloat16: _lib.DCMOE_BF16}
 
@@ -84,6 +84,15 @@ class Workspace:
             self.row_scale = torch.zeros(self.shapes["row_scale"], dtype=torch.float32, device=dev)
         self.slot_of = torch.empty((max(T, 1), dims.n_real), dtype=torch.int32, device=dev)
         self.row_token = torch.full((self.row_capacity,), -1, dtype=torch.int32, device=dev)
+        self._c_ws = None
+
+    def c_workspace(self) -> DcmoeWorkspace:
+        """The dcmoe_workspace struct of this workspace's buffers (built once; the buffers never move)."""
+        if self._c_ws is None:
+            self._c_ws = DcmoeWorkspace(self.plan.data_ptr(), self.x_packed.data_ptr(), self.slot_of.data_ptr(),
+                                        self.row_token.data_ptr(), self.row_scale.data_ptr(), self.h.data_ptr(),
+                                        self.y.data_ptr())
+        return self._c_ws
 
     # typed views into the plan buffer (device tensors; reading them on the host synchronises)
     def _view(self, off: int, n: int, dt: torch.dtype) -> torch.Tensor:
@@ -192,6 +201,30 @@ def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] =
         _lib.check(lib.dcmoe_combine_aux(_ptr(ws.y), _ptr(ws.slot_of), ws.T, ws.cfg, _ptr(residual), _ptr(out),
                                          ws.plan.data_ptr() + ws.layout.aux_loss, _ptr(aux_out), _stream()),
                    "dcmoe_combine_aux")
+
+
+def forward(x: torch.Tensor, w_gate: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Workspace, out: torch.Tensor,
+            attention_mask: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, impl: int = 0):
+    """The whole layer in ONE host call (``dcmoe_forward``).  Returns (logits, top_k, mask, gw, aux)."""
+    import ctypes
+
+    lib = _lib.load()
+    dims, T, dt, dev = ws.dims, ws.T, ws.dtype, ws.device
+    E = dims.n_experts
+    logits = torch.empty((T, E), dtype=dt, device=dev)
+    top_k = torch.empty((T,), dtype=torch.int64, device=dev)
+    mask = torch.empty((T, E), dtype=torch.int32, device=dev)
+    gw = torch.empty((T, E), dtype=dt, device=dev)
+    aux = torch.empty((), dtype=torch.float32, device=dev)
+    am = None
+    if attention_mask is not None:
+        am = attention_mask.reshape(-1).to(device=dev, dtype=torch.int32).contiguous()
+        if am.numel() != T:
+            raise ValueError("attention_mask must have one entry per token")
+    _lib.check(lib.dcmoe_forward(_ptr(x), _ptr(w_gate), _ptr(am), _ptr(w13), _ptr(w2), T, ws.row_capacity, ws.cfg,
+                                 ctypes.byref(ws.c_workspace()), _ptr(residual), _ptr(out), _ptr(logits), _ptr(top_k),
+                                 _ptr(mask), _ptr(gw), _ptr(aux), impl, _stream()), "dcmoe_forward")
+    return logits, top_k, mask, gw, aux
 
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, out: Optional[torch.Tensor] = None):
