@@ -44,6 +44,25 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 }
 #endif
 
+// "done once per device" flags for per-device function attributes (cudaFuncSetAttribute is per device; a process may
+// drive several GPUs).  Returns true the first time it is called for the current device with this flag set.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        const bool f = !done[dev];
+        done[dev] = true;
+        return f;
+    }
+    void reset_current() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) done[dev] = false;
+    }
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

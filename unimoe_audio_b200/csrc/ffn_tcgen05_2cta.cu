@@ -330,15 +330,14 @@ int launch_ffn_tcgen05_2cta(const void* x, const void* x_packed, const void* w13
     if (T == 0) return DCMOE_OK;
     const int H = cfg->hidden_size, Id = cfg->dynamic_intermediate_size;
     const int G = cfg->n_real + 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         int rc = check_cuda(cudaFuncSetAttribute(ffn_gemm2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                             "cudaFuncSetAttribute(gemm1 2cta)");
-        if (rc) return rc;
+        if (rc) { attr_once.reset_current(); return rc; }
         rc = check_cuda(cudaFuncSetAttribute(ffn_gemm2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                         "cudaFuncSetAttribute(gemm2 2cta)");
-        if (rc) return rc;
-        attr_set = true;
+        if (rc) { attr_once.reset_current(); return rc; }
     }
     CUtensorMap m_x, m_xp, m_w13, m_w13h, m_h_st, m_h_ld, m_w2, m_y_st;
     int rc;

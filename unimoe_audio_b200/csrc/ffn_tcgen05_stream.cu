@@ -430,15 +430,14 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     }
     const int H = cfg->hidden_size, Id = cfg->dynamic_intermediate_size;
     const int G = (ep_n_loc > 0 ? ep_n_loc : cfg->n_real) + 1;   // weight groups in the packs handed in
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         int rc = check_cuda(cudaFuncSetAttribute(ffn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                             "cudaFuncSetAttribute(stream gemm1)");
-        if (rc) return rc;
+        if (rc) { attr_once.reset_current(); return rc; }
         rc = check_cuda(cudaFuncSetAttribute(ffn_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES),
                         "cudaFuncSetAttribute(stream gemm2)");
-        if (rc) return rc;
-        attr_set = true;
+        if (rc) { attr_once.reset_current(); return rc; }
     }
     const int a_box = T <= 16 ? 16 : (T <= 32 ? 32 : 64);
     CUtensorMap m_x, m_xp, m_h, m_w13[4], m_w2[4];

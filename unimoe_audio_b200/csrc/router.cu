@@ -1136,14 +1136,13 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     const int router_smem = router_smem_bytes(cfg->hidden_size, rc.E);
     if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
         router_smem <= 232448) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.first()) {
             const int max_smem = router_smem_bytes(2048, 16) > 232448 ? 232448 : router_smem_bytes(2048, 16);
             int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<9,11>)");
-            if (rc2) return rc2;
+            if (rc2) { attr_once.reset_current(); return rc2; }
             rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<0,0>)");
-            if (rc2) return rc2;
-            attr_done = true;
+            if (rc2) { attr_once.reset_current(); return rc2; }
         }
         CUtensorMap tmap;
         int rc2 = make_tensor_map_bf16(&tmap, x, T, cfg->hidden_size, kRouterBlock);

@@ -87,15 +87,23 @@ _DEFAULT_BF16_IMPL = int(__import__("os").environ.get("DCMOE_FFN_IMPL", "0"))
 _WORKSPACES: Dict[tuple, Workspace] = {}
 
 
+def _workspace_bytes(ws: Workspace) -> int:
+    return sum(t.numel() * t.element_size() for t in (ws.plan, ws.h, ws.x_packed, ws.y, ws.row_scale, ws.slot_of, ws.row_token))
+
+
 def get_workspace(dims: LayerDims, dtype: torch.dtype, T: int, device, row_capacity: int = 0) -> Workspace:
-    """Workspaces are shared between layers (the 36 decoder layers run back to back on one stream)."""
+    """Workspaces are shared between layers (the 36 decoder layers run back to back on one stream) and kept per token
+    count: least recently used first out, at most 16 of them and 8 GiB in total (decode-sized ones are ~16 MB, a
+    16,384-token one ~2 GB)."""
     key = (dims, dtype, T, torch.device(device), row_capacity)
-    ws = _WORKSPACES.get(key)
+    ws = _WORKSPACES.pop(key, None)
     if ws is None:
-        if len(_WORKSPACES) >= 4:
-            _WORKSPACES.pop(next(iter(_WORKSPACES)))
         ws = Workspace(dims, dtype, T, device, row_capacity)
-        _WORKSPACES[key] = ws
+        need = _workspace_bytes(ws)
+        while _WORKSPACES and (len(_WORKSPACES) >= 16 or
+                               need + sum(_workspace_bytes(w) for w in _WORKSPACES.values()) > (8 << 30)):
+            _WORKSPACES.pop(next(iter(_WORKSPACES)))
+    _WORKSPACES[key] = ws          # (re)insert at the most-recently-used end
     return ws
 
 
