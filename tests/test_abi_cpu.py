@@ -100,3 +100,32 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert "route_oracle" not in text.replace("oracle/route_oracle.c", ""), f
+
+
+@pytest.mark.parametrize("gpg", [172, 128, 16, 40])          # I_d / 16, H / 16 of the reference config; small generic sizes
+@pytest.mark.parametrize("grid", [148, 132, 100, 37, 9])
+def test_weight_streaming_partition_covers_every_granule_once(gpg, grid):
+    """The CTA -> (m-tile, granule range) map of the decode-sized GEMMs (host mirror of cta_segment): every granule of
+    every hit weight group is computed by exactly one CTA, the CTAs of a group differ by at most one granule, and no
+    segment is wider than the bound the launcher sizes its ring stages with."""
+    for n_m in range(1, 10):
+        if n_m > grid:
+            continue
+        seg = ops.stream_segments(n_m, gpg, grid)
+        assert len(seg) == grid
+        cover = {m: [0] * gpg for m in range(n_m)}
+        sizes = {m: [] for m in range(n_m)}
+        for m, g0, ng in seg:
+            if ng == 0:
+                continue
+            assert 0 <= m < n_m and 0 <= g0 and g0 + ng <= gpg
+            for g in range(g0, g0 + ng):
+                cover[m][g] += 1
+            sizes[m].append(ng)
+        assert all(c == 1 for m in cover for c in cover[m])
+        ctas = [sum(1 for mm, _g, _n in seg if mm == m) for m in range(n_m)]
+        assert max(ctas) - min(ctas) <= 1                              # CTAs dealt evenly to the groups
+        for m in range(n_m):
+            assert max(sizes[m]) - min(sizes[m]) <= 1
+        bound = -(-gpg // (grid // 9)) if grid >= 9 else gpg            # launcher: ceil(gpg / floor(grid / G)), G = 9
+        assert max(max(v) for v in sizes.values()) <= max(bound, 1)

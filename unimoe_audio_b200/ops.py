@@ -227,6 +227,27 @@ def forward(x: torch.Tensor, w_gate: torch.Tensor, w13: torch.Tensor, w2: torch.
     return logits, top_k, mask, gw, aux
 
 
+def stream_segments(n_mtiles: int, granules_per_tile: int, grid: int):
+    """Host mirror of ``cta_segment`` (csrc/ffn_tcgen05_stream.cu): the (m-tile, first granule, granule count) every CTA
+    of the weight-streaming GEMMs works on.  CTAs are dealt to the m-tiles as evenly as possible, and the CTAs of one
+    m-tile cut its granules evenly.  Used by the CPU tests to pin the partition's invariants."""
+    out = []
+    n_m = min(n_mtiles, grid)
+    for c in range(grid):
+        if n_m <= 0:
+            out.append((0, 0, 0))
+            continue
+        base, extra = divmod(grid, n_m)
+        if c < extra * (base + 1):
+            m, idx, n = c // (base + 1), c % (base + 1), base + 1
+        else:
+            c2 = c - extra * (base + 1)
+            m, idx, n = extra + c2 // base, c2 % base, base
+        g0 = granules_per_tile * idx // n
+        out.append((m, g0, granules_per_tile * (idx + 1) // n - g0))
+    return out
+
+
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, out: Optional[torch.Tensor] = None):
     """Qwen2RMSNorm of [T, H] rows (the decoder layer's post_attention_layernorm, model.py:240)."""
     lib = _lib.load()
