@@ -174,8 +174,9 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *                128 x 256 tiles).  impl 0 selects them by itself when T <= 64 (see bit 20; DCMOE_FFN_STREAM=0 disables)
  *   phase        low 4 bits: 0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
  *                put CUDA events between the two launches.  Bits 4-5 select the tile group (tcgen05 only):
- *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism
- *                runs the shared experts while the dispatch is still in flight.  Bits 8-19: cap on the number of
+ *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only, 3 = the shared tiles from the
+ *                split point on (bits 28-30: split point in eighths of the shared tiles, impl 0; group 1 then stops
+ *                there) -- expert parallelism runs the shared experts while the dispatch / combine gather are in flight.  Bits 8-19: cap on the number of
  *                persistent CTAs (0 = one per SM), to leave SMs to concurrently running dispatch / combine kernels.
  *                Bits 21-24 / 25-27 (impl 3): expert-parallel decode -- n_loc and rank: the plan and x_packed cover all
  *                experts (replicated routing of the gathered tokens), w13 / w2 hold this rank's n_loc routed experts as

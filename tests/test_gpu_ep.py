@@ -33,6 +33,9 @@ def test_local_ranks_match_single_gpu(setup, world, tokens, split):
     gen = torch.Generator().manual_seed(sum(tokens) + world)
     xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
     lr = LocalRanks(m, world, split=split)
+    if split and world == 4:
+        for ep in lr.ranks:           # also exercise the optional split of the shared experts' GEMM-1 (tile groups 1 / 3)
+            ep.shared_split = 4
     outs = lr.forward(xs)
     torch.cuda.synchronize()
     x_all = torch.cat(xs, dim=1)

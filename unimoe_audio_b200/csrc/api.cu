@@ -153,7 +153,7 @@ int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void*
 int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
                     const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
-                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, int, cudaStream_t);
 int launch_rmsnorm(const void*, const void*, double, int64_t, const dcmoe_config*, void*, cudaStream_t);
 bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int, int);
 int launch_ffn_tcgen05_stream(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
@@ -286,6 +286,7 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     const int max_ctas = (phase >> 8) & 0xfff;   // bits 8-19: cap on the persistent grid (0 = one CTA per SM)
     const int ep_n_loc = (phase >> 21) & 15;     // bits 21-24 / 25-27 (impl 3 only): expert-parallel decode -- the plan covers
     const int ep_rank = (phase >> 25) & 7;       // all experts, w13 / w2 hold this rank's ep_n_loc routed experts + the shared pair
+    const int shared_split = (phase >> 28) & 7;  // bits 28-30 (impl 0): split point of the shared tiles in eighths (0 = none)
     const bool no_decode = (phase >> 20) & 1;    // bit 20: never pick the decode kernels (expert parallelism: a rank
                                                  // can own more rows than it has tokens)
     phase &= 15;
@@ -315,7 +316,8 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
                                        max_ctas, (cudaStream_t)stream);
     }
     if (impl == 0) return launch_ffn_tcgen05(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
-                                             phase, group_sel, max_ctas, (cudaStream_t)stream);
+                                             phase, group_sel, max_ctas, shared_split, (cudaStream_t)stream);
+    if (shared_split != 0 || group_sel == 3) { set_error("shared-tile split is implemented by impl 0 only"); return DCMOE_ERR_INVALID; }
     if (impl == 1) {
         if (sz.max_mtiles > 65535) { set_error("CUDA-core FFN: too many row tiles (%lld)", (long long)sz.max_mtiles); return DCMOE_ERR_INVALID; }
         if (group_sel != 0) { set_error("CUDA-core FFN does not support tile-group selection"); return DCMOE_ERR_INVALID; }

@@ -130,6 +130,11 @@ class ExpertParallelDCMoE:
         self.overlap = os.environ.get("DCMOE_EP_OVERLAP", "1") != "0"   # comm stream under the shared experts' GEMMs
         self.comm_ctas = int(os.environ.get("DCMOE_EP_COMM_CTAS", "148"))   # grid cap of dispatch / partial combine (0 = full)
         self.gemm_ctas = int(os.environ.get("DCMOE_EP_GEMM_CTAS", "0"))   # CTAs of the shared GEMMs that run under comm (0 = all SMs)
+        # eighths of the shared experts' GEMM-1 that run under the dispatch, the rest then runs with GEMM-2 under the
+        # combine gather; 0 = all of it under the dispatch.  Measured at 8 GPUs with 4/8: no gain (5.19 vs 4.86 ms per
+        # step) -- the gather and the GEMMs compete for the same SMs and HBM, the gather just stretches from 0.70 to
+        # 1.15 ms -- so the split stays off by default
+        self.shared_split = int(os.environ.get("DCMOE_EP_SHARED_SPLIT", "0"))
         self._side = None
         self.comm_events = []        # (name, start, end) CUDA events of the comm-stream kernels, filled when a stage hook is set
         self._local_cfg = None
@@ -249,8 +254,10 @@ class ExpertParallelDCMoE:
                                          ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
                                          ws.slot_of.data_ptr(), max_ctas, st), "dcmoe_ep_dispatch")
 
-    def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0):
-        """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2 = all / shared-expert / routed row tiles."""
+    def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0,
+                  shared_split: int = 0):
+        """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2/3 = all / shared-expert / routed row tiles / the shared
+        tiles from the split point on; shared_split s (1..7): split point at s/8 of the shared tiles (group 1 stops there)."""
         lib = _lib.load()
         ws = self.ws
         if self._local_cfg is None:
@@ -261,7 +268,7 @@ class ExpertParallelDCMoE:
         _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
                                          self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, self._local_cfg,
                                          ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl,
-                                         phase | (group_sel << 4) | (max_ctas << 8) | (1 << 20), st),
+                                         phase | (group_sel << 4) | (max_ctas << 8) | (1 << 20) | (shared_split << 28), st),
                    "dcmoe_grouped_ffn")
         if name and self.m.stage_hook:
             self.m.stage_hook(name)
@@ -427,7 +434,8 @@ class ExpertParallelDCMoE:
                     self.comm_events.append(("ep_dispatch", t0, t1))
                 dist.all_reduce(self._flag2, group=self.group)                   # barrier 1 (on the comm stream)
                 ev[1].record(side)
-            self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas)             # overlaps the dispatch
+            ss = self.shared_split if self.m.ffn_impl in (None, 0) else 0
+            self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas, ss)         # overlaps the dispatch (first ss/8 of the tiles)
             main.wait_event(ev[1])
             hook("wait_dispatch")
             self.phase_ffn(1, 2, "ffn_gemm1_routed")
@@ -445,7 +453,9 @@ class ExpertParallelDCMoE:
                     t3.record(side)
                     self.comm_events.append(("ep_combine_gather", t2, t3))
                 ev[3].record(side)
-            self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)             # overlaps the combine gather
+            if ss:                                                               # rest of the shared GEMM-1 + GEMM-2 overlap
+                self.phase_ffn(1, 3, "ffn_gemm1_shared_rest", self.gemm_ctas, ss)   # the combine gather
+            self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)
             main.wait_event(ev[3])
             hook("wait_combine")
             self.phase_combine(out.view(T, H), 2)
@@ -520,7 +530,7 @@ class LocalRanks:
                 outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
         else:   # the kernel sequence of the overlapped schedule (run serially here)
             for ep in self.ranks:
-                ep.phase_ffn(1, 1)          # shared GEMM-1 needs nothing from the dispatch
+                ep.phase_ffn(1, 1, shared_split=ep.shared_split)   # (part of the) shared GEMM-1 needs nothing from the dispatch
             for ep in self.ranks:
                 ep.phase_dispatch()
             for ep in self.ranks:
@@ -529,6 +539,8 @@ class LocalRanks:
             for ep in self.ranks:
                 ep.phase_combine(None, 1)
             for ep in self.ranks:
+                if ep.shared_split:
+                    ep.phase_ffn(1, 3, shared_split=ep.shared_split)
                 ep.phase_ffn(2, 1)
             outs = []
             for r, ep in enumerate(self.ranks):
