@@ -584,7 +584,9 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
                  : "r"(addr));
 }
 
-template <int NDYN, int NE>
+// DBG: per-role cycle counters (DCMOE_ROUTER_DEBUG=1) -- a separate instantiation, so that the production kernel keeps
+// its 56 registers (with the counters compiled in it needed 64 and spilled)
+template <int NDYN, int NE, bool DBG>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat16* __restrict__ wg,
                   const int32_t* __restrict__ attn_mask, int64_t T, int H, int n_blocks, RouteConsts rc,
@@ -606,6 +608,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
     auto x_full = [&](int s) { return bars + 8u * s; };
     auto x_empty = [&](int s) { return bars + 8u * (kXStages + s); };
 
+    unsigned long long* const dbg = DBG ? rc.dbg : nullptr;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = NE ? NE : rc.E;
     const int n_dyn = NDYN ? NDYN : rc.n_dyn;
@@ -619,7 +622,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         fence_barrier_init();
     }
     __syncthreads();   // barriers initialised
-    const long long t_begin = rc.dbg ? clock64() : 0;
+    const long long t_begin = dbg ? clock64() : 0;
     int prod_it = 0;
     if (warp == 0) {
         // the producer puts the first stages in flight before anyone stages W_g
@@ -686,7 +689,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
     // W_g fragments staged: a barrier of the 28 consumer warps only -- the producer is still issuing its first 64
     // boxes (~60 cycles each in the TMA unit) and needs nothing from this phase (barrier 0 is not used again)
     if (warp != 0) named_bar_sync(0, kTmaThreads - 32);
-    const long long t_staged = rc.dbg ? clock64() : 0;
+    const long long t_staged = dbg ? clock64() : 0;
     long long d0 = 0, d1 = 0, d2 = 0;
     constexpr int kFullCount = 128 + 256;   // gate warps + one routing group
     if (warp == 0) {
@@ -695,9 +698,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
         for (int blk = blockIdx.x + prod_it * gridDim.x; blk < n_blocks; blk += gridDim.x, ++it) {
             const int st = it & (kXStages - 1);
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
-            const long long q0 = rc.dbg ? clock64() : 0;
+            const long long q0 = dbg ? clock64() : 0;
             mbar_wait(x_empty(st), ph ^ 1u);
-            if (rc.dbg) d0 += clock64() - q0;
+            if (dbg) d0 += clock64() - q0;
             if (lane == 0) mbar_expect_tx(x_full(st), (uint32_t)(kRouterBlock * H * 2));
             __syncwarp();
             for (int c = lane; c < n_chunks; c += 32)
@@ -718,9 +721,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const uint32_t ph = (uint32_t)(it / kXStages) & 1u;
             const int rs = it % kRedStages;
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            const long long q0 = rc.dbg ? clock64() : 0;
+            const long long q0 = dbg ? clock64() : 0;
             mbar_wait(x_full(st), ph);
-            const long long q1 = rc.dbg ? clock64() : 0;
+            const long long q1 = dbg ? clock64() : 0;
             for (int cc = 0; cc < chunks_per_warp; ++cc) {
                 const int c = wq * chunks_per_warp + cc;
                 const uint32_t tile = xs + st * kXStageBytes + c * (kRouterBlock * 128);
@@ -738,9 +741,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(x_empty(st));           // this warp is done reading the x stage
-            const long long q2 = rc.dbg ? clock64() : 0;
+            const long long q2 = dbg ? clock64() : 0;
             if (it >= kRedStages) named_bar_sync(7 + rs, kFullCount);
-            if (rc.dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
+            if (dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
             float* r = red + ((rs * 4 + wq) * kRouterBlock) * 16;
             r[g * 16 + 2 * tq] = c0[0];
             r[g * 16 + 2 * tq + 1] = c0[1];
@@ -752,12 +755,12 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             r[(g + 8) * 16 + 8 + 2 * tq + 1] = c1[3];
             named_bar_arrive(1 + rs, kFullCount);
         }
-        if (rc.dbg && warp == 1 && lane == 0) {
-            rc.dbg[blockIdx.x * 16 + 2] = d0;
-            rc.dbg[blockIdx.x * 16 + 3] = d1;
-            rc.dbg[blockIdx.x * 16 + 4] = d2;
-            rc.dbg[blockIdx.x * 16 + 10] = it;
-            rc.dbg[blockIdx.x * 16 + 11] = clock64() - t_begin;   // gate warps done
+        if (dbg && warp == 1 && lane == 0) {
+            dbg[blockIdx.x * 16 + 2] = d0;
+            dbg[blockIdx.x * 16 + 3] = d1;
+            dbg[blockIdx.x * 16 + 4] = d2;
+            dbg[blockIdx.x * 16 + 10] = it;
+            dbg[blockIdx.x * 16 + 11] = clock64() - t_begin;   // gate warps done
         }
     } else {
         // ================= routing warps: group g = warps 5+8g .. 12+8g =================
@@ -773,9 +776,9 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             const int tl = rw_ * 2 + half;
             const int64_t t = tok0 + tl;
             const bool valid = t < T;
-            const long long q0 = rc.dbg ? clock64() : 0;
+            const long long q0 = dbg ? clock64() : 0;
             named_bar_sync(1 + rs, kFullCount);
-            const long long q1 = rc.dbg ? clock64() : 0;
+            const long long q1 = dbg ? clock64() : 0;
             float l = 0.0f;
             if (j < E) {
                 const float* r = red + (rs * 4 * kRouterBlock + tl) * 16 + j;
@@ -787,7 +790,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
             int raw, mk;
             float gw, ga;
             route_token<true, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
-            const long long q2 = rc.dbg ? clock64() : 0;
+            const long long q2 = dbg ? clock64() : 0;
             if (valid && j < E) {
                 logits_out[t * E + j] = __float2bfloat16_rn(l);
                 gw_out[t * E + j] = __float2bfloat16_rn(gw);
@@ -811,19 +814,19 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
                 block_counts[(int64_t)blk * n_dyn + gtid] = c;
                 block_probs[(int64_t)blk * n_dyn + gtid] = pr;
             }
-            if (rc.dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
+            if (dbg) { d0 += q1 - q0; d1 += q2 - q1; d2 += clock64() - q2; }
         }
-        if (rc.dbg && warp == 5 && lane == 0) {
-            rc.dbg[blockIdx.x * 16 + 5] = d0;
-            rc.dbg[blockIdx.x * 16 + 6] = d1;
-            rc.dbg[blockIdx.x * 16 + 7] = d2;
-            rc.dbg[blockIdx.x * 16 + 8] = clock64() - t_begin;   // routing group 0 done
-            rc.dbg[blockIdx.x * 16 + 9] = t_staged - t_begin;
+        if (dbg && warp == 5 && lane == 0) {
+            dbg[blockIdx.x * 16 + 5] = d0;
+            dbg[blockIdx.x * 16 + 6] = d1;
+            dbg[blockIdx.x * 16 + 7] = d2;
+            dbg[blockIdx.x * 16 + 8] = clock64() - t_begin;   // routing group 0 done
+            dbg[blockIdx.x * 16 + 9] = t_staged - t_begin;
         }
     }
-    if (rc.dbg && warp == 0 && lane == 0) {
-        rc.dbg[blockIdx.x * 16 + 0] = d0;
-        rc.dbg[blockIdx.x * 16 + 1] = clock64() - t_begin;       // producer done
+    if (dbg && warp == 0 && lane == 0) {
+        dbg[blockIdx.x * 16 + 0] = d0;
+        dbg[blockIdx.x * 16 + 1] = clock64() - t_begin;       // producer done
     }
 }
 
@@ -1139,9 +1142,10 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         static PerDeviceOnce attr_once;
         if (attr_once.first()) {
             const int max_smem = router_smem_bytes(2048, 16) > 232448 ? 232448 : router_smem_bytes(2048, 16);
-            int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<9,11>)");
+            int rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<9,11>)");
             if (rc2) { attr_once.reset_current(); return rc2; }
-            rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<0,0>)");
+            rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<0,0>)");
+            if (!rc2) rc2 = check_cuda(cudaFuncSetAttribute(router_tma_kernel<9, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute(router_tma<9,11,dbg>)");
             if (rc2) { attr_once.reset_current(); return rc2; }
         }
         CUtensorMap tmap;
@@ -1155,15 +1159,19 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
             cudaMemsetAsync(dbg, 0, 256 * 16 * sizeof(unsigned long long), stream);
             rc.dbg = dbg;
         }
-        if (ref_shape)
-            router_tma_kernel<9, 11><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+        if (ref_shape && debug)     // the counters exist for the reference shape only
+            router_tma_kernel<9, 11, true><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
+                (__nv_bfloat16*)global_weight, block_counts, block_probs);
+        else if (ref_shape)
+            router_tma_kernel<9, 11, false><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
                 (__nv_bfloat16*)global_weight, block_counts, block_probs);
         else
-            router_tma_kernel<0, 0><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
+            router_tma_kernel<0, 0, false><<<g2, b2, router_smem, stream>>>(tmap, (const __nv_bfloat16*)w_gate, attn_mask, T,
                 cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
                 (__nv_bfloat16*)global_weight, block_counts, block_probs);
-        if (debug) {   // tuning only: synchronises
+        if (debug && ref_shape) {   // tuning only: synchronises
             static int printed = 0;
             cudaStreamSynchronize(stream);
             static unsigned long long host[256 * 16];
