@@ -86,7 +86,7 @@ class HostPipeline:
 
 class GraphedDCMoE:
     """CUDA-graph replay of one DCMoE forward for a fixed token count (decode steps: T = 2N tokens per call,
-    36 layers x up to 1000 steps -- reference model.py:1149-1203).  The forward is launch-only (six kernels, no
+    36 layers x up to 1000 steps -- reference model.py:1149-1203).  The forward is launch-only (four to six kernels, no
     host synchronisation, all data-dependent sizes in the device-side plan), so it captures as is; a replay costs
     one cudaGraphLaunch instead of six launches plus the Python around them.
 
