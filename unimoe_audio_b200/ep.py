@@ -143,6 +143,8 @@ class ExpertParallelDCMoE:
         # local experts' rows computed by the weight-streaming kernels, combine over peer memory (see decode_forward)
         self.decode_mode = os.environ.get("DCMOE_EP_DECODE", "1") != "0"
         self._dws: Optional[EpWorkspace] = None
+        self._dws_by_T = {}
+        self._dy_raw = None               # (ptr, bytes) of the peer-visible y of the decode-sized path
         self._dpeer = None
         self._dflag = None
 
@@ -290,11 +292,31 @@ class ExpertParallelDCMoE:
                 and self.m.ffn_impl in (None, 0, 3))
 
     def ensure_decode_workspace(self, T_total: int, device, ipc: bool) -> EpWorkspace:
-        if self._dws is None or self._dws.T != T_total:
-            self._dws = EpWorkspace(self.m.dims, torch.bfloat16, T_total, device, 0, ipc)     # worst-case rows for T_total tokens
-            self._dws.x_all = torch.empty((T_total, self.m.dims.hidden_size), dtype=torch.bfloat16, device=device)
-            self._dpeer = None
-        return self._dws
+        """Workspace of a decode-sized call on T_total gathered tokens (kept per token count).  Across processes the
+        only peer-visible buffer is y; it is allocated ONCE, for 64 tokens, and every per-T workspace views it, so the
+        cudaIpc handles are exchanged a single time however the batch size varies."""
+        ws = self._dws_by_T.get(T_total)
+        if ws is None:
+            if len(self._dws_by_T) >= 8:
+                self._dws_by_T.pop(next(iter(self._dws_by_T)))
+            ws = EpWorkspace(self.m.dims, torch.bfloat16, T_total, device, 0, False)      # worst-case rows for T_total tokens
+            ws.x_all = torch.empty((T_total, self.m.dims.hidden_size), dtype=torch.bfloat16, device=device)
+            if ipc:
+                H = self.m.dims.hidden_size
+                if self._dy_raw is None:
+                    lib = _lib.load()
+                    sizes, _ = ops.query_sizes(self.m.dims, torch.bfloat16, 64, 0)
+                    nbytes = int(sizes.row_capacity) * H * 2
+                    p = ctypes.c_void_p()
+                    with torch.cuda.device(device):
+                        _lib.check(lib.dcmoe_ipc_alloc(nbytes, ctypes.byref(p)), "dcmoe_ipc_alloc")
+                    self._dy_raw = (p.value, nbytes)
+                assert ws.row_capacity * H * 2 <= self._dy_raw[1]
+                ws.y = _wrap(self._dy_raw[0], ws.row_capacity * H * 2, torch.bfloat16, (ws.row_capacity, H), ws.device)
+                ws._c_ws = None
+            self._dws_by_T[T_total] = ws
+        self._dws = ws
+        return ws
 
     def set_decode_peers(self, y: List[int]):
         self._dpeer = (ctypes.c_void_p * len(y))(*y)
@@ -303,17 +325,18 @@ class ExpertParallelDCMoE:
         import torch.distributed as dist
 
         lib = _lib.load()
-        mine = self._dws.export_handles()
+        buf = (ctypes.c_uint8 * 64)()
+        _lib.check(lib.dcmoe_ipc_export(self._dy_raw[0], buf), "dcmoe_ipc_export")
         allh = [None] * self.world
-        dist.all_gather_object(allh, mine, group=self.group)
+        dist.all_gather_object(allh, bytes(buf), group=self.group)
         ys = []
         for r in range(self.world):
             if r == self.rank:
-                ys.append(self._dws._raw["y"][0])
+                ys.append(self._dy_raw[0])
             else:
                 p = ctypes.c_void_p()
-                buf = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r]["y"])
-                _lib.check(lib.dcmoe_ipc_import(buf, ctypes.byref(p)), "dcmoe_ipc_import")
+                hb = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r])
+                _lib.check(lib.dcmoe_ipc_import(hb, ctypes.byref(p)), "dcmoe_ipc_import")
                 self._imported.append(p.value)
                 ys.append(p.value)
         self.set_decode_peers(ys)
