@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DCMOE_ABI_VERSION 1
+#define DCMOE_ABI_VERSION 2
 
 typedef enum dcmoe_dtype { DCMOE_F32 = 0, DCMOE_BF16 = 1 } dcmoe_dtype;
 
@@ -87,10 +87,6 @@ typedef struct dcmoe_plan_layout {
     int64_t aux_loss;       /* [1] float                 audio_load_balancing_loss_func result     */
     int64_t mtiles;         /* [max_mtiles] dcmoe_mtile                                          */
     int64_t overflow;       /* [1] int32                 1 if the rows did not fit row_capacity (tiles dropped!)  */
-    int64_t n_pairs;        /* [1] int32                 number of valid entries in pairs          */
-    int64_t pairs;          /* [max_mtiles] int32        tile pairs for the 2-CTA GEMM: index of the first */
-                            /*                           m-tile | (1 << 30 if the next tile of the same   */
-                            /*                           group completes the 256-row pair)              */
     int64_t total;          /* == plan_bytes */
 } dcmoe_plan_layout;
 
@@ -167,16 +163,15 @@ int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_
  *   w2           [n_real+1, H, I_d] D
  *   h            [row_capacity, I_d] D    silu(gate) * up * row_scale   (scratch)
  *   y            [row_capacity, H] D      already weighted expert outputs
- *   impl         0 = tcgen05/TMEM/TMA grouped GEMM, one CTA per tile (bf16 only); 2 = the same on CTA pairs
- *                (tcgen05.mma.cta_group::2, 256-row tiles); 1 = CUDA-core fp32-accumulate GEMM (the fp32 layer
- *                path; also usable with bf16 for cross-checking); 3 = weight-streaming tcgen05 GEMMs for decode-sized
- *                calls (bf16, T <= 64: weights as the MMA M operand, one K pass per SM; h and y bit-equal to impl 0's
- *                128 x 256 tiles).  impl 0 selects them by itself when T <= 64 (see bit 20; DCMOE_FFN_STREAM=0 disables)
+ *   impl         0 = tcgen05/TMEM/TMA grouped GEMM, one CTA per 128 x 256 tile (bf16 only); 1 = CUDA-core
+ *                fp32-accumulate GEMM (the fp32 layer path; also usable with bf16 for cross-checking); 3 = weight-streaming
+ *                tcgen05 GEMMs for decode-sized calls (bf16, T <= 64: weights as the MMA M operand, one K pass per SM; h
+ *                and y bit-equal to impl 0's tiles).  impl 0 selects them by itself when T <= 64 (see bit 20;
+ *                DCMOE_FFN_STREAM=0 disables)
  *   phase        low 4 bits: 0 = both GEMMs, 1 = GEMM-1 only (x -> h), 2 = GEMM-2 only (h -> y); lets a caller
  *                put CUDA events between the two launches.  Bits 4-5 select the tile group (tcgen05 only):
- *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only, 3 = the shared tiles from the
- *                split point on (bits 28-30: split point in eighths of the shared tiles, impl 0; group 1 then stops
- *                there) -- expert parallelism runs the shared experts while the dispatch / combine gather are in flight.  Bits 8-19: cap on the number of
+ *                0 = every row tile, 1 = shared-expert tiles only, 2 = routed tiles only -- expert parallelism runs the
+ *                shared experts while the dispatch / combine gather are in flight.  Bits 8-19: cap on the number of
  *                persistent CTAs (0 = one per SM), to leave SMs to concurrently running dispatch / combine kernels.
  *                Bits 21-24 / 25-27 (impl 3): expert-parallel decode -- n_loc and rank: the plan and x_packed cover all
  *                experts (replicated routing of the gathered tokens), w13 / w2 hold this rank's n_loc routed experts as
@@ -292,6 +287,35 @@ int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* glo
 int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32_t* slot_of, int64_t T,
                      const dcmoe_config* cfg, int world, int mode, float* partial, void* out, int max_ctas,
                      void* stream);
+
+/*
+ * Stream-ordered barrier of the expert-parallel group over peer memory, optionally carrying a payload (instead of NCCL:
+ * the all-gather of the per-rank counts, the all-gather of decode-sized token rows, the 4-byte all-reduces used as
+ * barriers).  Every rank allocates int32 flags[DCMOE_EP_FLAG_SLOTS][DCMOE_MAX_RANKS] with dcmoe_ipc_alloc (zeroed), maps
+ * the peers' arrays, and calls this with the same (slot, epoch) on every rank, epoch increasing from call to call.
+ * Work enqueued on `stream` after the call sees everything every rank's stream wrote -- to its own or to peer memory --
+ * before that rank's call, and (payload_bytes > 0) holds every rank's payload: rank q's `payload` lands at
+ * peer_payload_dst[r] + q * payload_bytes on every rank r (an all-gather into buffers the ranks mapped beforehand).
+ * peer_flags / peer_payload_dst: HOST arrays of `world` device pointers (entry `rank` = own buffers).
+ * payload_bytes must be a multiple of 4.  The wait is bounded (~20 s), then the kernel traps.
+ */
+#define DCMOE_EP_FLAG_SLOTS 8
+int dcmoe_ep_barrier(int32_t* const* peer_flags, int rank, int world, int slot, int32_t epoch, const void* payload,
+                     int64_t payload_bytes, void* const* peer_payload_dst, void* stream);
+
+/*
+ * Weight-gather expert parallelism (large token counts): the experts stay sharded in HBM (core.py:505: rank r holds
+ * experts [r*n_loc, (r+1)*n_loc) + the replicated shared pack as w13 / w2 packs of n_loc + 1 groups), but instead of
+ * sending every routed ROW to its expert's owner and back (core.py:467, :480: ~ T_loc * r * 8 KB per layer), each rank
+ * pulls the remote experts' packed WEIGHTS ((world-1)/world * 270 MB per layer) into a staging pack of all n_real + 1
+ * groups and runs the single-GPU forward on its own tokens: no dispatch, no combine exchange, no load imbalance when
+ * the routing is skewed.  One cudaMemcpyAsync per peer and matrix (copy engines over NVLink, no SM involved), enqueued
+ * on `stream`; peers are visited in ring order so that every GPU is read by one peer at a time.
+ *   peer_w13 / peer_w2   HOST arrays of `world` device pointers to the ranks' packs (cudaIpc-mapped; entry `rank` = own)
+ *   w13_full / w2_full   [n_real + 1, 2*I_d, H] / [n_real + 1, H, I_d] D   (cfg describes the FULL layer)
+ */
+int dcmoe_ep_fetch_weights(const void* const* peer_w13, const void* const* peer_w2, int rank, int world,
+                           const dcmoe_config* cfg, void* w13_full, void* w2_full, void* stream);
 
 #ifdef __cplusplus
 }

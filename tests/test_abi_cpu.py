@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dcmoe_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
-    assert lib.dcmoe_abi_version() == 1
+    assert lib.dcmoe_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_query_sizes_reference_config():

@@ -64,3 +64,19 @@ def test_gloo_world2_count_exchange_gives_consistent_layouts():
     for e in range(8):
         assert l1[0][e] == l0[0][e] + t0[0][e]
         assert l0[1][e] == l1[1][e]
+
+
+def test_choose_path_thresholds():
+    """Host logic that picks the expert-parallel path of a call: decode (replicated tokens) for world * T <= 64 in bf16,
+    weight gather from gather_min_tokens on, the token dispatch in between; the mode switch forces one of the two."""
+    from unimoe_audio_b200.ep import choose_path
+    bf, f32 = torch.bfloat16, torch.float32
+    assert choose_path(8, 8, bf) == "decode" and choose_path(9, 8, bf) == "dispatch"
+    assert choose_path(8, 8, f32) == "dispatch"                       # the decode kernels are bf16 only
+    assert choose_path(8, 8, bf, decode_ok=False) == "dispatch"
+    assert choose_path(8191, 4, bf) == "dispatch" and choose_path(8192, 4, bf) == "gather"
+    assert choose_path(100, 2, bf, mode="gather") == "gather" and choose_path(1 << 20, 2, bf, mode="dispatch") == "dispatch"
+    assert choose_path(32, 2, bf, mode="gather") == "decode"          # decode-sized calls keep their own path
+    assert choose_path(0, 2, bf) == "dispatch"
+    # every configs[3] point (64 x 4096 tokens over 2 / 4 / 8 ranks) is a weight-gather call
+    assert all(choose_path(64 * 4096 // r, r, bf) == "gather" for r in (2, 4, 8))

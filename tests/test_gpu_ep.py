@@ -33,9 +33,6 @@ def test_local_ranks_match_single_gpu(setup, world, tokens, split):
     gen = torch.Generator().manual_seed(sum(tokens) + world)
     xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
     lr = LocalRanks(m, world, split=split)
-    if split and world == 4:
-        for ep in lr.ranks:           # also exercise the optional split of the shared experts' GEMM-1 (tile groups 1 / 3)
-            ep.shared_split = 4
     outs = lr.forward(xs)
     torch.cuda.synchronize()
     x_all = torch.cat(xs, dim=1)
@@ -61,6 +58,54 @@ def test_local_ranks_match_single_gpu(setup, world, tokens, split):
         assert meta[:8] == dest_base and meta[16:24] == dest_tpad
         assert ep.ws.seg_base.cpu().tolist()[: n_loc + 1] == seg
         assert ep.ws.counts.cpu().tolist()[:n_loc] == tot
+
+
+@pytest.mark.parametrize("world,tokens", [(2, [300, 300]), (4, [257, 16, 1, 130]), (8, [64] * 8)])
+def test_weight_gather_path_matches_single_gpu(setup, world, tokens):
+    """Weight-gather expert parallelism on virtual ranks: every rank copies all ranks' packs into its staging pack
+    (dcmoe_ep_fetch_weights) and runs the single-GPU forward on its own rows -> each rank's 6-tuple (except the aux loss,
+    which is per rank) is bit-equal to the single-GPU layer on the concatenated batch.  Called twice with different
+    inputs: the second call uses the other staging slot and must not see stale weights or rows."""
+    from unimoe_audio_b200.ep import LocalRanks
+    m, W, dev, dt = setup
+    lr = LocalRanks(m, world)
+    for rep in range(2):
+        gen = torch.Generator().manual_seed(sum(tokens) + world + 1000 * rep)
+        xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
+        outs = lr.gather_forward(xs)
+        torch.cuda.synchronize()
+        ref = m(torch.cat(xs, dim=1), None, None)
+        torch.cuda.synchronize()
+        off = 0
+        for r, t in enumerate(tokens):
+            o = outs[r]
+            for i in (1, 2, 3, 4):
+                assert torch.equal(o[i], ref[i][off:off + t]), (rep, r, i)
+            assert torch.equal(o[0][0], ref[0][0, off:off + t]), f"call {rep} rank {r} output differs"
+            off += t
+    # the staging pack of rank 0 now equals the single-GPU pack, group by group
+    m.pack_weights()
+    ctx = lr.ranks[0].ctx
+    assert any(torch.equal(w13, m._w13) and torch.equal(w2, m._w2) for w13, w2 in ctx.stage)
+
+
+def test_dispatch_workspace_is_reused_across_token_counts(setup):
+    """a later call with MORE tokens than the first one must not reuse buffers sized for the first call
+    (the fp32 partial sums of the overlapped combine used to be allocated once)."""
+    from unimoe_audio_b200.ep import LocalRanks
+    m, W, dev, dt = setup
+    lr = LocalRanks(m, 2, split=True)
+    for tokens in ([256, 256], [1024, 1000], [100, 90]):
+        gen = torch.Generator().manual_seed(sum(tokens))
+        xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
+        outs = lr.forward(xs)
+        torch.cuda.synchronize()
+        ref = m(torch.cat(xs, dim=1), None, None)
+        off = 0
+        for r, t in enumerate(tokens):
+            assert torch.equal(outs[r][0][0], ref[0][0, off:off + t]), (tokens, r)
+            assert outs[r][0].shape[1] == t and lr.ranks[r].ws.partial.shape[0] >= t
+            off += t
 
 
 def test_local_ranks_oracle_parity(setup):

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcmoe_b200.so")
 
 DCMOE_F32, DCMOE_BF16 = 0, 1
+ABI_VERSION = 2
 ROUTER_BLOCK, TILE_M = 16, 128
 
 
@@ -36,7 +37,7 @@ class DcmoeSizes(Structure):
 
 class DcmoePlanLayout(Structure):
     _fields_ = [(n, c_int64) for n in ("block_counts", "block_probs", "block_offsets", "counts", "seg_base",
-                                       "n_mtiles", "aux_loss", "mtiles", "overflow", "n_pairs", "pairs", "total")]
+                                       "n_mtiles", "aux_loss", "mtiles", "overflow", "total")]
 
 
 class DcmoeError(RuntimeError):
@@ -78,6 +79,9 @@ SIGNATURES = {
                                   c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_void_p]),
     "dcmoe_ep_combine": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_int64, POINTER(DcmoeConfig), c_int, c_int,
                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "dcmoe_ep_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int32, c_void_p, c_int64, POINTER(c_void_p), c_void_p]),
+    "dcmoe_ep_fetch_weights": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, POINTER(DcmoeConfig), c_void_p,
+                                       c_void_p, c_void_p]),
 }
 
 
@@ -100,7 +104,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError = ABI mismatch, fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.dcmoe_abi_version() != 1:
+    if lib.dcmoe_abi_version() != ABI_VERSION:
         raise DcmoeError("libdcmoe_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -131,8 +131,6 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     l->aux_loss = off;     off = align_up(off + 4, 16);
     l->mtiles = off;       off = align_up(off + sz->max_mtiles * (int64_t)sizeof(dcmoe_mtile), 16);
     l->overflow = off;     off = align_up(off + 4, 16);
-    l->n_pairs = off;      off = align_up(off + 4, 16);
-    l->pairs = off;        off = align_up(off + sz->max_mtiles * 4, 16);
     l->total = off;
     sz->plan_bytes = off;
     return DCMOE_OK;
@@ -153,13 +151,24 @@ int ep_plan_view(const dcmoe_config* cfg, int64_t T, int64_t row_capacity, void*
 int launch_ffn_simt(const void*, const void*, const void*, const void*, const float*, int64_t, const dcmoe_config*,
                     const dcmoe_sizes&, PlanView, void*, void*, int, int, cudaStream_t);
 int launch_ffn_tcgen05(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
-                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, int, cudaStream_t);
+                       const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
 int launch_rmsnorm(const void*, const void*, double, int64_t, const dcmoe_config*, void*, cudaStream_t);
 bool ffn_stream_applicable(int64_t, const dcmoe_config*, const dcmoe_sizes&, int, int);
 int launch_ffn_tcgen05_stream(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
                               const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, int, cudaStream_t);
-int launch_ffn_tcgen05_2cta(const void*, const void*, const void*, const void*, const float*, int64_t, int64_t,
-                            const dcmoe_config*, const dcmoe_sizes&, PlanView, void*, void*, int, int, int, cudaStream_t);
+
+int device_sm_count() {
+    static int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
 
 bool pdl_enabled() {
     static const bool on = [] {
@@ -286,7 +295,6 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
     const int max_ctas = (phase >> 8) & 0xfff;   // bits 8-19: cap on the persistent grid (0 = one CTA per SM)
     const int ep_n_loc = (phase >> 21) & 15;     // bits 21-24 / 25-27 (impl 3 only): expert-parallel decode -- the plan covers
     const int ep_rank = (phase >> 25) & 7;       // all experts, w13 / w2 hold this rank's ep_n_loc routed experts + the shared pair
-    const int shared_split = (phase >> 28) & 7;  // bits 28-30 (impl 0): split point of the shared tiles in eighths (0 = none)
     const bool no_decode = (phase >> 20) & 1;    // bit 20: never pick the decode kernels (expert parallelism: a rank
                                                  // can own more rows than it has tokens)
     phase &= 15;
@@ -310,14 +318,9 @@ int dcmoe_grouped_ffn(const void* x, const void* x_packed, const void* w13, cons
             return launch_ffn_tcgen05_stream(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase,
                                              max_ctas, 0, 0, (cudaStream_t)stream);
     }
-    if (impl == 2) {
-        if (cfg->dtype != DCMOE_BF16) { set_error("tcgen05 FFN is bf16 only"); return DCMOE_ERR_INVALID; }
-        return launch_ffn_tcgen05_2cta(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y, phase, group_sel,
-                                       max_ctas, (cudaStream_t)stream);
-    }
+    if (group_sel == 3) { set_error("dcmoe_grouped_ffn: tile group must be 0, 1 or 2"); return DCMOE_ERR_INVALID; }
     if (impl == 0) return launch_ffn_tcgen05(x, x_packed, w13, w2, row_scale, T, sz.row_capacity, cfg, sz, pv, h, y,
-                                             phase, group_sel, max_ctas, shared_split, (cudaStream_t)stream);
-    if (shared_split != 0 || group_sel == 3) { set_error("shared-tile split is implemented by impl 0 only"); return DCMOE_ERR_INVALID; }
+                                             phase, group_sel, max_ctas, (cudaStream_t)stream);
     if (impl == 1) {
         if (sz.max_mtiles > 65535) { set_error("CUDA-core FFN: too many row tiles (%lld)", (long long)sz.max_mtiles); return DCMOE_ERR_INVALID; }
         if (group_sel != 0) { set_error("CUDA-core FFN does not support tile-group selection"); return DCMOE_ERR_INVALID; }

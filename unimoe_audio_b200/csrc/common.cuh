@@ -63,6 +63,9 @@ struct PerDeviceOnce {
     }
 };
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs) -- api.cu
+int device_sm_count();
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
@@ -77,8 +80,6 @@ struct PlanView {
     float* aux_loss;
     dcmoe_mtile* mtiles;
     int32_t* overflow;
-    int32_t* n_pairs;
-    int32_t* pairs;
 };
 
 inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
@@ -93,8 +94,6 @@ inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
     v.aux_loss = reinterpret_cast<float*>(p + l.aux_loss);
     v.mtiles = reinterpret_cast<dcmoe_mtile*>(p + l.mtiles);
     v.overflow = reinterpret_cast<int32_t*>(p + l.overflow);
-    v.n_pairs = reinterpret_cast<int32_t*>(p + l.n_pairs);
-    v.pairs = reinterpret_cast<int32_t*>(p + l.pairs);
     return v;
 }
 

@@ -13,6 +13,7 @@
 //     128-bit peer loads (ld.global.nc over NVLink), adds the local shared-expert row in fp32, one store.
 // The only host-visible collectives are an all-gather of (n_real + 1) int32 per rank and two 4-byte
 // all-reduces used as stream-ordered barriers (NCCL, issued from Python).
+#include <cstdio>
 #include <cstring>
 
 #include "common.cuh"
@@ -31,7 +32,7 @@ struct EpPeers {
 
 // ep_meta (device int32): [0,16) dest_base[e]  row-space row ON THE OWNER where this rank's rows of expert e start
 //                         [16,32) dest_tpad[e]  t_pad of the owner of expert e
-constexpr int kEpMetaInts = 32;
+static_assert(DCMOE_EP_META_INTS == 32, "ep_meta layout");
 
 namespace {
 
@@ -111,35 +112,6 @@ __global__ void __launch_bounds__(256) ep_plan_kernel(const int32_t* __restrict_
         }
         pv.mtiles[i] = mt;
     }
-    // tile pairs for the 2-CTA GEMM: consecutive m-tiles of one group, two at a time
-    {
-        __shared__ int s_pair0[kMaxDyn + 2];
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            s_pair0[0] = 0;                                   // group order: shared tiles, then segments 0..n_loc-1
-            acc += (n_shared_tiles + 1) / 2;
-            for (int e = 0; e < n_loc; ++e) {
-                s_pair0[e + 1] = acc;
-                acc += (s_tile0[e + 1] - s_tile0[e] + 1) / 2;
-            }
-            s_pair0[n_loc + 1] = acc;
-            *pv.n_pairs = acc < max_mtiles ? acc : max_mtiles;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < total && i < max_mtiles; i += blockDim.x) {
-            int start, pbase, end;
-            if (i < n_shared_tiles) { start = 0; pbase = s_pair0[0]; end = n_shared_tiles; }
-            else {
-                int e = 0;
-                while (e + 1 < n_loc && i >= s_tile0[e + 1]) ++e;
-                start = s_tile0[e]; pbase = s_pair0[e + 1]; end = s_tile0[e + 1];
-            }
-            if (((i - start) & 1) == 0) {
-                const int pi = pbase + ((i - start) >> 1);
-                if (pi < max_mtiles) pv.pairs[pi] = i | ((i + 1 < end) ? (1 << 30) : 0);
-            }
-        }
-    }
 }
 
 // shared-expert row scales (gw[t, n_dyn], gw[t, n_dyn + 1]) of the local rows [0, T): written here, before the
@@ -164,7 +136,7 @@ __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict
                                                           int n_dyn, int n_fix, int n_loc, int rank,
                                                           const int32_t* __restrict__ block_offsets,
                                                           const int32_t* __restrict__ ep_meta, EpPeers peers,
-                                                          int32_t* __restrict__ slot_of, int n_blocks) {
+                                                          int32_t* __restrict__ slot_of, int n_blocks, int row_limit) {
     __shared__ int s_m[kRouterBlock][kMaxDyn];
     __shared__ int s_slot[kRouterBlock][kMaxDyn];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -190,10 +162,14 @@ __global__ void __launch_bounds__(128) ep_dispatch_kernel(const char* __restrict
         int slot = -1;
         if (s_m[tl][e]) {
             slot = ep_meta[e] + block_offsets[(int64_t)blk * n_real + e] + rk;   // row on the owner
-            const float w = load_gw(t, e);
-            float* sc = peers.row_scale[e / n_loc];
-            sc[2 * (int64_t)slot] = w;
-            sc[2 * (int64_t)slot + 1] = w;
+            if (slot >= row_limit) {
+                slot = -1;     // beyond the owner's row capacity (every rank uses the same): dropped, plan.overflow = 1 there
+            } else {
+                const float w = load_gw(t, e);
+                float* sc = peers.row_scale[e / n_loc];
+                sc[2 * (int64_t)slot] = w;
+                sc[2 * (int64_t)slot + 1] = w;
+            }
         }
         s_slot[tl][e] = slot;
         if (t < T) slot_of[t * n_real + e] = slot;
@@ -374,6 +350,55 @@ __global__ void __launch_bounds__(256, 3) ep_combine_kernel(const char* __restri
     }  // token loop
 }
 
+// Cross-GPU barrier over peer memory, optionally carrying a payload (replaces the NCCL collectives of the
+// expert-parallel paths: the all-gather of the per-rank counts, the all-gather of decode-sized token rows and the
+// 4-byte all-reduces used as stream-ordered barriers).
+// Every rank owns a flag array int32[DCMOE_EP_FLAG_SLOTS][DCMOE_MAX_RANKS] mapped into all ranks.  CTA r of rank q
+// copies the payload (if any) into rank r's buffer at offset q * payload_bytes, publishes `epoch` into rank r's
+// flags[slot][q] (fence.sc.sys + st.release.sys: the payload AND everything this rank's EARLIER kernels on the stream
+// wrote -- to local or peer memory -- is visible to whoever acquires the flag), then waits until its own
+// flags[slot][r] has reached `epoch` (ld.acquire.sys).  Kernels launched after this one on the stream therefore see
+// every rank's payload and every rank's writes from before its barrier call.  The spin is bounded (trap, no hang).
+struct EpFlagPeers {
+    int32_t* flags[kMaxRanks];
+    char* payload_dst[kMaxRanks];
+};
+
+__global__ void __launch_bounds__(256) ep_barrier_kernel(EpFlagPeers peers, int rank, int world, int slot, int32_t epoch,
+                                                         const char* __restrict__ payload, int64_t payload_bytes) {
+    const int r = blockIdx.x;   // peer this CTA talks to
+    if (payload != nullptr && payload_bytes > 0) {
+        char* dst = peers.payload_dst[r] + (int64_t)rank * payload_bytes;
+        if (((payload_bytes | (int64_t)(uintptr_t)dst | (int64_t)(uintptr_t)payload) & 15) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(payload);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (int64_t i = threadIdx.x; i < payload_bytes / 16; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            const int32_t* s1 = reinterpret_cast<const int32_t*>(payload);
+            int32_t* d1 = reinterpret_cast<int32_t*>(dst);
+            for (int64_t i = threadIdx.x; i < payload_bytes / 4; i += blockDim.x) d1[i] = s1[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    asm volatile("fence.sc.sys;" ::: "memory");
+    int32_t* dstf = peers.flags[r] + slot * kMaxRanks + rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dstf), "r"(epoch) : "memory");
+    const int32_t* src = peers.flags[rank] + slot * kMaxRanks + r;
+    const long long t0 = clock64();
+    for (;;) {
+        int32_t v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        __nanosleep(64);
+        if (clock64() - t0 > 40000000000ll) {   // ~20 s: a rank that never arrives must not hang the GPU
+            printf("dcmoe: expert-parallel barrier timed out (rank %d waiting for rank %d, slot %d, epoch %d, saw %d)\n",
+                   rank, r, slot, epoch, v);
+            __trap();
+        }
+    }
+}
+
 }  // namespace
 
 // single-GPU combine = the expert-parallel combine with one rank (peers.y[0] = y)
@@ -482,10 +507,10 @@ int dcmoe_ep_dispatch(const void* x, const int32_t* expert_mask, const void* glo
     dim3 grid((unsigned)nb), block(128);
     if (cfg->dtype == DCMOE_BF16)
         ep_dispatch_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
-            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks);
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks, (int)(sz.max_mtiles * kTileM));
     else
         ep_dispatch_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>((const char*)x, expert_mask, (const char*)global_weight,
-            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks);
+            T, cfg->hidden_size, cfg->n_real, n_dyn, cfg->n_fix, cfg->n_real / world, rank, pv.block_offsets, ep_meta, peers, slot_of, (int)sz.n_blocks, (int)(sz.max_mtiles * kTileM));
     return check_cuda(cudaGetLastError(), "ep_dispatch_kernel launch");
 }
 
@@ -514,6 +539,60 @@ int dcmoe_ep_combine(const void* y_local, const void* const* peer_y, const int32
     else { if (bf16) DCMOE_EP_COMBINE(true, 2); else DCMOE_EP_COMBINE(false, 2); }
 #undef DCMOE_EP_COMBINE
     return check_cuda(cudaGetLastError(), "ep_combine_kernel launch");
+}
+
+int dcmoe_ep_barrier(int32_t* const* peer_flags, int rank, int world, int slot, int32_t epoch, const void* payload,
+                     int64_t payload_bytes, void* const* peer_payload_dst, void* stream) {
+    if (!peer_flags || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || slot < 0 || slot >= DCMOE_EP_FLAG_SLOTS ||
+        payload_bytes < 0 || (payload_bytes & 3) != 0 || (payload_bytes > 0 && (!payload || !peer_payload_dst))) {
+        set_error("dcmoe_ep_barrier: bad arguments (world=%d rank=%d slot=%d payload_bytes=%lld)", world, rank, slot,
+                  (long long)payload_bytes);
+        return DCMOE_ERR_INVALID;
+    }
+    EpFlagPeers peers{};
+    for (int r = 0; r < world; ++r) {
+        if (!peer_flags[r] || (payload_bytes > 0 && !peer_payload_dst[r])) {
+            set_error("dcmoe_ep_barrier: NULL pointer for rank %d", r);
+            return DCMOE_ERR_INVALID;
+        }
+        peers.flags[r] = peer_flags[r];
+        peers.payload_dst[r] = payload_bytes > 0 ? (char*)peer_payload_dst[r] : nullptr;
+    }
+    ep_barrier_kernel<<<world, 256, 0, (cudaStream_t)stream>>>(peers, rank, world, slot, epoch,
+                                                               payload_bytes > 0 ? (const char*)payload : nullptr, payload_bytes);
+    return check_cuda(cudaGetLastError(), "ep_barrier_kernel launch");
+}
+
+int dcmoe_ep_fetch_weights(const void* const* peer_w13, const void* const* peer_w2, int rank, int world,
+                           const dcmoe_config* cfg, void* w13_full, void* w2_full, void* stream) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (!peer_w13 || !peer_w2 || !w13_full || !w2_full || world < 1 || world > kMaxRanks || rank < 0 || rank >= world ||
+        cfg->n_real % world != 0) {
+        set_error("dcmoe_ep_fetch_weights: bad arguments (world=%d rank=%d n_real=%d)", world, rank, cfg->n_real);
+        return DCMOE_ERR_INVALID;
+    }
+    const int64_t es = cfg->dtype == DCMOE_BF16 ? 2 : 4;
+    const int n_loc = cfg->n_real / world;
+    const int64_t g13 = 2ll * cfg->dynamic_intermediate_size * cfg->hidden_size * es;   // bytes of one weight group of W13
+    const int64_t g2 = (int64_t)cfg->hidden_size * cfg->dynamic_intermediate_size * es; // ... of W2
+    cudaStream_t st = (cudaStream_t)stream;
+    auto copy = [&](void* dst, const void* src, int64_t bytes, const char* what) {
+        return check_cuda(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, st), what);
+    };
+    // the shared pack (group n_loc of every rank's pack; taken from this rank's own) goes first: the shared experts'
+    // row tiles head the tile list
+    if ((rc = copy((char*)w13_full + cfg->n_real * g13, (const char*)peer_w13[rank] + n_loc * g13, g13, "copy of the shared W13"))) return rc;
+    if ((rc = copy((char*)w2_full + cfg->n_real * g2, (const char*)peer_w2[rank] + n_loc * g2, g2, "copy of the shared W2"))) return rc;
+    // then the ranks' routed experts, starting with this rank's own and walking the ring: at any moment every rank
+    // is read by ONE other rank, so no GPU's NVLink egress is shared between readers
+    for (int i = 0; i < world; ++i) {
+        const int q = (rank + i) % world;
+        if (!peer_w13[q] || !peer_w2[q]) { set_error("dcmoe_ep_fetch_weights: NULL weight pointer for rank %d", q); return DCMOE_ERR_INVALID; }
+        if ((rc = copy((char*)w13_full + (int64_t)q * n_loc * g13, peer_w13[q], n_loc * g13, "peer copy of W13"))) return rc;
+        if ((rc = copy((char*)w2_full + (int64_t)q * n_loc * g2, peer_w2[q], n_loc * g2, "peer copy of W2"))) return rc;
+    }
+    return DCMOE_OK;
 }
 
 }  // extern "C"

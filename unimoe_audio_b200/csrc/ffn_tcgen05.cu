@@ -264,22 +264,11 @@ ffn_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x     
     }
 }
 
-// ------------------------------------------------------------------ host side
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
-}
-
 }  // namespace
 
 int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, const void* w2, const float* row_scale,
                        int64_t T, int64_t row_capacity, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv,
-                       void* h, void* y, int phase, int group_sel, int max_ctas, int shared_split, cudaStream_t stream) {
+                       void* h, void* y, int phase, int group_sel, int max_ctas, cudaStream_t stream) {
     if (T == 0) return DCMOE_OK;
     if (cfg->dtype != DCMOE_BF16) {
         set_error("tcgen05 FFN is bf16 only (fp32 layers use the CUDA-core path, impl = 1)");
@@ -320,15 +309,11 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
     p1.mtiles = pv.mtiles;
     p1.n_mtiles = pv.n_mtiles;
     p1.row_scale = row_scale;
-    // group_sel: 0 = every m-tile, 1 = shared-expert tiles only, 2 = routed tiles only (shared tiles come first),
-    // 3 = the shared tiles from the split point on; shared_split s in 1..7 puts that point at s/8 of the shared tiles
-    // and makes group_sel 1 stop there (expert parallelism hides the dispatch under the first part and the combine
-    // gather under the second part + GEMM-2)
+    // group_sel: 0 = every m-tile, 1 = shared-expert tiles only, 2 = routed tiles only (shared tiles come first):
+    // expert parallelism runs the shared experts while remote rows / remote weights are still in flight
     const int n_shared_tiles = (int)(sz.t_pad / BM);
-    const int split_at = shared_split > 0 ? (int)((int64_t)n_shared_tiles * shared_split / 8) : n_shared_tiles;
-    if (group_sel == 3 && shared_split <= 0) { set_error("tile group 3 needs a shared split (phase bits 28-30)"); return DCMOE_ERR_INVALID; }
-    p1.m_begin = group_sel == 2 ? n_shared_tiles : (group_sel == 3 ? split_at : 0);
-    p1.m_end = group_sel == 1 ? split_at : (group_sel == 3 ? n_shared_tiles : -1);
+    p1.m_begin = group_sel == 2 ? n_shared_tiles : 0;
+    p1.m_end = group_sel == 1 ? n_shared_tiles : -1;
     p2 = p1;
     p2.n_tiles = (int)ceil_div(H, bn);
     p2.n_last = H - (p2.n_tiles - 1) * bn;
@@ -337,7 +322,7 @@ int launch_ffn_tcgen05(const void* x, const void* x_packed, const void* w13, con
 
     // DCMOE_FFN_MAX_CTAS (debug / tuning): run the persistent GEMMs on fewer SMs than the chip has, e.g. to leave
     // SMs to the expert-parallel dispatch / combine kernels that run concurrently
-    int n_ctas = num_sms();
+    int n_ctas = device_sm_count();
     if (max_ctas > 0 && max_ctas < n_ctas) n_ctas = max_ctas;
     dim3 grid((unsigned)n_ctas), block(NUM_THREADS);
     if (phase != 2) {

@@ -391,16 +391,6 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
     }
 }
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
-}
-
 }  // namespace
 
 bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, int max_ctas, int ep_n_loc) {
@@ -409,7 +399,7 @@ bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes
     if (!(cfg->dtype == DCMOE_BF16 && T > 0 && T <= 64 && sz.t_pad == BM && cfg->dynamic_intermediate_size % GR == 0 &&
           cfg->shared_intermediate_size % GR == 0 && cfg->hidden_size % GR == 0))
         return false;
-    int n_ctas = sm_count();
+    int n_ctas = device_sm_count();
     if (max_ctas > 0 && max_ctas < n_ctas) n_ctas = max_ctas;
     const int G = (ep_n_loc > 0 ? ep_n_loc : cfg->n_real) + 1;   // most weight groups one launch can work on
     if (n_ctas < G) return false;
@@ -451,7 +441,7 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
         if ((rc = make_tensor_map_bf16(&m_w2[i], w2, (int64_t)G * H, Id, GR << i))) return rc;
     }
 
-    int n_ctas = sm_count();
+    int n_ctas = device_sm_count();
     if (max_ctas > 0 && max_ctas < n_ctas) n_ctas = max_ctas;
 
     StreamParams p1, p2;

@@ -144,42 +144,13 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         }
         pv.mtiles[i] = mt;
     }
-    // tile pairs for the 2-CTA GEMM: consecutive m-tiles of one group, two at a time
-    {
-        __shared__ int s_pair0[kMaxDyn + 2];
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            s_pair0[0] = 0;                                   // group order: shared tiles, then segments 0..n_real-1
-            acc += (n_shared_tiles + 1) / 2;
-            for (int e = 0; e < n_real; ++e) {
-                s_pair0[e + 1] = acc;
-                acc += (s_tile0[e + 1] - s_tile0[e] + 1) / 2;
-            }
-            s_pair0[n_real + 1] = acc;
-            *pv.n_pairs = acc < max_mtiles ? acc : max_mtiles;
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < total && i < max_mtiles; i += blockDim.x) {
-            int start, pbase, end;
-            if (i < n_shared_tiles) { start = 0; pbase = s_pair0[0]; end = n_shared_tiles; }
-            else {
-                int e = 0;
-                while (e + 1 < n_real && i >= s_tile0[e + 1]) ++e;
-                start = s_tile0[e]; pbase = s_pair0[e + 1]; end = s_tile0[e + 1];
-            }
-            if (((i - start) & 1) == 0) {
-                const int pi = pbase + ((i - start) >> 1);
-                if (pi < max_mtiles) pv.pairs[pi] = i | ((i + 1 < end) ? (1 << 30) : 0);
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int ESIZE>  // bytes per element
 __global__ void __launch_bounds__(128) permute_kernel(const char* __restrict__ x, const int32_t* __restrict__ mask,
                                                       const char* __restrict__ gw, int64_t T, int H, int n_real,
-                                                      int n_dyn, int n_fix, int t_pad, PlanView pv,
+                                                      int n_dyn, int n_fix, int t_pad, int row_limit, PlanView pv,
                                                       char* __restrict__ x_packed, int32_t* __restrict__ slot_of,
                                                       int32_t* __restrict__ row_token, float* __restrict__ row_scale) {
     __shared__ int s_m[kRouterBlock][kMaxDyn];
@@ -205,10 +176,14 @@ __global__ void __launch_bounds__(128) permute_kernel(const char* __restrict__ x
         int slot = -1;
         if (s_m[tl][e]) {
             slot = pv.seg_base[e] + pv.block_offsets[(int64_t)blockIdx.x * n_real + e] + rank;
-            row_token[slot] = (int32_t)t;
-            const float w = load_gw(t, e);
-            row_scale[2 * (int64_t)slot] = w;
-            row_scale[2 * (int64_t)slot + 1] = w;
+            if (slot >= row_limit) {
+                slot = -1;     // row_capacity below the worst case and exceeded: the row is dropped (plan.overflow = 1)
+            } else {
+                row_token[slot] = (int32_t)t;
+                const float w = load_gw(t, e);
+                row_scale[2 * (int64_t)slot] = w;
+                row_scale[2 * (int64_t)slot + 1] = w;
+            }
         }
         s_slot[tl][e] = slot;
         if (t < T) slot_of[t * n_real + e] = slot;
@@ -304,11 +279,11 @@ int launch_permute(const void* x, const int32_t* expert_mask, const void* gw, in
     dim3 grid((unsigned)sz.n_blocks), block(128);
     if (cfg->dtype == DCMOE_BF16)
         permute_kernel<2><<<grid, block, 0, stream>>>((const char*)x, expert_mask, (const char*)gw, T, cfg->hidden_size,
-                                                      cfg->n_real, n_dyn, cfg->n_fix, (int)sz.t_pad, pv,
+                                                      cfg->n_real, n_dyn, cfg->n_fix, (int)sz.t_pad, (int)(sz.max_mtiles * kTileM), pv,
                                                       (char*)x_packed, slot_of, row_token, row_scale);
     else
         permute_kernel<4><<<grid, block, 0, stream>>>((const char*)x, expert_mask, (const char*)gw, T, cfg->hidden_size,
-                                                      cfg->n_real, n_dyn, cfg->n_fix, (int)sz.t_pad, pv,
+                                                      cfg->n_real, n_dyn, cfg->n_fix, (int)sz.t_pad, (int)(sz.max_mtiles * kTileM), pv,
                                                       (char*)x_packed, slot_of, row_token, row_scale);
     return check_cuda(cudaGetLastError(), "permute_kernel launch");
 }

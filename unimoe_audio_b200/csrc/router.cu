@@ -423,134 +423,11 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised persistent router (bf16): the gate projection is HBM bound, the routing maths is
-// latency / issue bound.  In the one-CTA-per-block kernel above every CTA of the (single) wave streams x first
-// and routes afterwards, so the two phases of the whole grid run back to back.  Here each CTA keeps 8 "gate"
-// warps streaming x for successive token blocks (two groups of 4 warps, K split four ways, 8 x 16 B per lane in
-// flight) and 8 "routing" warps consuming the logits through a 4-stage smem ring, so HBM traffic and the
-// shuffle/exp chains overlap for the whole kernel.  Named barriers (bar.arrive / bar.sync) hand the stages over.
-constexpr int kWsStages = 4;
-constexpr int kWsThreads = 512;
-
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-template <int NDYN, int NE>
-__global__ void __launch_bounds__(kWsThreads, 2)
-router_ws_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wg,
-                 const int32_t* __restrict__ attn_mask, int64_t T, int H, int n_blocks, RouteConsts rc,
-                 __nv_bfloat16* __restrict__ logits_out, int64_t* __restrict__ top_k,
-                 int32_t* __restrict__ expert_mask, __nv_bfloat16* __restrict__ gw_out,
-                 int32_t* __restrict__ block_counts, float* __restrict__ block_probs) {
-    __shared__ float red[kWsStages][4][kRouterBlock][16];
-    __shared__ int s_cnt[2][kRouterBlock][kMaxDyn];
-    __shared__ float s_prob[2][kRouterBlock][kMaxDyn];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int E = NE ? NE : rc.E;
-    const int n_dyn = NDYN ? NDYN : rc.n_dyn;
-    constexpr int kFullCount = 128 + 256;   // one gate group + the routing warps
-    // barrier ids: 1..4 full[s], 5..8 empty[s], 9 routing-internal
-    if (warp < 8) {
-        // ================= gate warps =================
-        const int grp = warp >> 2, wq = warp & 3;
-        const int Kq = H >> 2, k0 = wq * Kq;
-        const int g = lane >> 2, tq = lane & 3;
-        const bool wv0 = g < E, wv1 = g + 8 < E;
-        const __nv_bfloat16* w0 = wg + (int64_t)(wv0 ? g : 0) * H + k0 + tq * 8;
-        const __nv_bfloat16* w1 = wg + (int64_t)(wv1 ? g + 8 : 0) * H + k0 + tq * 8;
-        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-        const int steps = Kq >> 5;
-        int it = grp;
-        for (int blk = blockIdx.x + grp * gridDim.x; blk < n_blocks; blk += 2 * gridDim.x, it += 2) {
-            const int st = it & (kWsStages - 1);
-            const int64_t tok0 = (int64_t)blk * kRouterBlock;
-            const int64_t r0 = tok0 + g, r1 = r0 + 8;
-            const bool v0 = r0 < T, v1 = r1 < T;
-            const __nv_bfloat16* xr0 = x + (v0 ? r0 : 0) * (int64_t)H + k0 + tq * 8;
-            const __nv_bfloat16* xr1 = x + (v1 ? r1 : 0) * (int64_t)H + k0 + tq * 8;
-            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int s0 = 0; s0 < steps; s0 += 4) {
-                uint4 a[4], b[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    a[u] = (v0 && s0 + u < steps) ? ld_nc_v4(xr0 + (s0 + u) * 32) : zero;   // zero past this warp's K range
-                    b[u] = (v1 && s0 + u < steps) ? ld_nc_v4(xr1 + (s0 + u) * 32) : zero;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 q0 = (wv0 && s0 + u < steps) ? ld_ca_v4(w0 + (s0 + u) * 32) : zero;
-                    uint4 q1 = (wv1 && s0 + u < steps) ? ld_ca_v4(w1 + (s0 + u) * 32) : zero;
-                    mma_bf16_16816(c0, a[u].x, b[u].x, a[u].y, b[u].y, q0.x, q0.y);
-                    mma_bf16_16816(c0, a[u].z, b[u].z, a[u].w, b[u].w, q0.z, q0.w);
-                    mma_bf16_16816(c1, a[u].x, b[u].x, a[u].y, b[u].y, q1.x, q1.y);
-                    mma_bf16_16816(c1, a[u].z, b[u].z, a[u].w, b[u].w, q1.z, q1.w);
-                }
-            }
-            if (it >= kWsStages) named_bar_sync(5 + st, kFullCount);   // routing warps released this stage
-            red[st][wq][g][2 * tq] = c0[0];
-            red[st][wq][g][2 * tq + 1] = c0[1];
-            red[st][wq][g + 8][2 * tq] = c0[2];
-            red[st][wq][g + 8][2 * tq + 1] = c0[3];
-            red[st][wq][g][8 + 2 * tq] = c1[0];
-            red[st][wq][g][8 + 2 * tq + 1] = c1[1];
-            red[st][wq][g + 8][8 + 2 * tq] = c1[2];
-            red[st][wq][g + 8][8 + 2 * tq + 1] = c1[3];
-            __threadfence_block();
-            named_bar_arrive(1 + st, kFullCount);
-        }
-    } else {
-        // ================= routing warps =================
-        const int rw_ = warp - 8;
-        const int half = lane >> 4, j = lane & 15;
-        const int rtid = tid - 256;
-        int it = 0;
-        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
-            const int st = it & (kWsStages - 1);
-            const int64_t tok0 = (int64_t)blk * kRouterBlock;
-            const int tl = rw_ * 2 + half;
-            const int64_t t = tok0 + tl;
-            const bool valid = t < T;
-            named_bar_sync(1 + st, kFullCount);
-            float l = 0.0f;
-            if (j < E) {
-                l = __fadd_rn(__fadd_rn(__fadd_rn(red[st][0][tl][j], red[st][1][tl][j]), red[st][2][tl][j]), red[st][3][tl][j]);
-                l = bf16_round(l);
-            }
-            // hand the stage back only if the gate group will write it again
-            if ((int64_t)blk + (int64_t)kWsStages * gridDim.x < n_blocks) named_bar_arrive(5 + st, kFullCount);
-            const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
-            int raw, mk;
-            float gw, ga;
-            route_token<true, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
-            const long long q2 = rc.dbg ? clock64() : 0;
-            if (valid && j < E) {
-                logits_out[t * E + j] = __float2bfloat16_rn(l);
-                gw_out[t * E + j] = __float2bfloat16_rn(gw);
-                expert_mask[t * E + j] = mk;
-                if (j == 0) top_k[t] = raw;
-            }
-            const int sb = it & 1;
-            s_cnt[sb][tl][j] = (valid && j < n_dyn) ? mk : 0;
-            s_prob[sb][tl][j] = (valid && j < n_dyn) ? ga : 0.0f;
-            named_bar_sync(9, 256);
-            if (rtid < n_dyn) {
-                int cnt = 0;
-                float pr = 0.0f;
-#pragma unroll
-                for (int r = 0; r < kRouterBlock; ++r) {
-                    cnt += s_cnt[sb][r][rtid];
-                    pr = __fadd_rn(pr, s_prob[sb][r][rtid]);
-                }
-                block_counts[(int64_t)blk * n_dyn + rtid] = cnt;
-                block_probs[(int64_t)blk * n_dyn + rtid] = pr;
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -836,7 +713,7 @@ router_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __nv_bfloat1
 // kernels above are pure launch + latency (14.7 + 6.6 + 6.6 us measured at T = 2).  Here one 32-warp CTA does the
 // gate projection (token block x K-eighth per warp, mma.sync), routes every token in a single round (32 warps x 2
 // tokens, the same route_token<> -> identical bits), builds the plan in shared memory (counts, segment bases, tile
-// table, pairs, aux) and gathers the selected rows into x_packed.
+// table, aux) and gathers the selected rows into x_packed.
 constexpr int kFrontMaxT = 64;
 
 template <int NDYN, int NE>
@@ -961,13 +838,12 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     if (rc.dbg && tid == 0) rc.dbg[6] = clock64() - t_fs0;
     if (tid == 0) {
         const int n_sh = t_pad / kTileM;
-        int row = t_pad, tile = 0, pair = 0;
+        int row = t_pad, tile = 0;
         for (int i = 0; i < n_sh && tile < max_mtiles; ++i, ++tile) {
             dcmoe_mtile mt;
             mt.a_row = i * kTileM; mt.out_row = i * kTileM; mt.group = n_real;
             mt.rows = min(kTileM, T - i * kTileM);
             pv.mtiles[tile] = mt;
-            if ((i & 1) == 0) pv.pairs[pair++] = tile | ((i + 1 < n_sh) ? (1 << 30) : 0);
         }
         for (int e = 0; e < n_real; ++e) {
             s_seg[e] = row;
@@ -978,15 +854,13 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
                 mt.out_row = row + i * kTileM; mt.a_row = mt.out_row - t_pad; mt.group = e;
                 mt.rows = min(kTileM, s_cnt[e] - i * kTileM);
                 pv.mtiles[tile] = mt;
-                if ((i & 1) == 0) pv.pairs[pair++] = tile | ((i + 1 < nt) ? (1 << 30) : 0);
             }
             row += nt * kTileM;
         }
         s_seg[n_real] = row;
         pv.seg_base[n_real] = row;
         *pv.n_mtiles = tile;
-        *pv.n_pairs = pair;
-        *pv.overflow = 0;
+        *pv.overflow = (row > max_mtiles * kTileM) ? 1 : 0;
         if (rc.dbg) rc.dbg[7] = clock64() - t_fs0;
     }
     if (tid >= 32 && tid < 32 + n_dyn) {
@@ -1025,9 +899,13 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         int slot = -1;
         if (s_mask[t][e]) {
             slot = s_seg[e] + rank;
-            row_token[slot] = t;
-            row_scale[2 * (int64_t)slot] = s_gw[t][e];
-            row_scale[2 * (int64_t)slot + 1] = s_gw[t][e];
+            if (slot >= max_mtiles * kTileM) {
+                slot = -1;     // row_capacity below the worst case and exceeded: dropped (plan.overflow = 1)
+            } else {
+                row_token[slot] = t;
+                row_scale[2 * (int64_t)slot] = s_gw[t][e];
+                row_scale[2 * (int64_t)slot + 1] = s_gw[t][e];
+            }
         }
         s_slot[t][e] = slot;
         slot_of[i] = slot;
@@ -1125,19 +1003,11 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
                                                            logits_out, top_k, expert_mask, global_weight,            \
                                                            block_counts, block_probs)
     const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
-    static int ws_mode_env = -1;
-    if (ws_mode_env < 0) {
-        const char* env = getenv("DCMOE_ROUTER_MODE");   // debug switch: 0 = one CTA per block, 1 = warp-specialised
-        ws_mode_env = env ? atoi(env) : 2;               // (register-staged loads), 2 = TMA-fed persistent (default)
-    }
-    int ws_mode = ws_mode_env;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     // (decode-sized calls were measured with the one-CTA-per-block kernel too: 21.8 us vs 14.7 us for the TMA-fed
     // kernel at T = 2, so the persistent kernel is used at every size)
     const int router_smem = router_smem_bytes(cfg->hidden_size, rc.E);
-    if (bf16 && logits_in == nullptr && ws_mode == 2 && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
+    if (bf16 && logits_in == nullptr && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
         router_smem <= 232448) {
         static PerDeviceOnce attr_once;
         if (attr_once.first()) {
@@ -1186,19 +1056,6 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
             }
         }
         return check_cuda(cudaGetLastError(), "router_tma_kernel launch");
-    }
-    if (bf16 && logits_in == nullptr && ws_mode >= 1) {
-        const int64_t want = 2 * (int64_t)sms;
-        dim3 g2((unsigned)(n_blocks < want ? n_blocks : want)), b2(kWsThreads);
-        if (ref_shape)
-            router_ws_kernel<9, 11><<<g2, b2, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask, T,
-                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
-                (__nv_bfloat16*)global_weight, block_counts, block_probs);
-        else
-            router_ws_kernel<0, 0><<<g2, b2, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w_gate, attn_mask, T,
-                cfg->hidden_size, (int)n_blocks, rc, (__nv_bfloat16*)logits_out, top_k, expert_mask,
-                (__nv_bfloat16*)global_weight, block_counts, block_probs);
-        return check_cuda(cudaGetLastError(), "router_ws_kernel launch");
     }
     if (bf16) {
         if (ref_shape) DCMOE_LAUNCH_ROUTER(true, 9, 11); else DCMOE_LAUNCH_ROUTER(true, 0, 0);

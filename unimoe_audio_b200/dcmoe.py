@@ -81,9 +81,6 @@ class _MoE(nn.Module):              # UniMoEAudioMoE, core.py:496-523
                                        self.num_local_experts)
 
 
-# bf16 FFN implementation: 0 = tcgen05 one CTA per 128-row tile, 2 = tcgen05 CTA pairs (cta_group::2, 256-row tiles)
-_DEFAULT_BF16_IMPL = int(__import__("os").environ.get("DCMOE_FFN_IMPL", "0"))
-
 _WORKSPACES: Dict[tuple, Workspace] = {}
 
 
@@ -159,7 +156,12 @@ class DCMoE(nn.Module):
         self._w2: Optional[torch.Tensor] = None
         self._packed_key = None
         self.ffn_impl = ffn_impl          # None: tcgen05 for bf16, CUDA-core for fp32
-        self.row_capacity = 0             # 0 = worst case
+        self.row_capacity = 0             # rows of the FFN workspace; 0 = from row_capacity_factor
+        # routed rows per token the workspace is sized for; None = worst case (n_real: every token to every routed
+        # expert -- ~2 GB at 16,384 tokens, 8 GB at 65,536).  Top-P 0.7 routing averages 3.6; with a factor below n_real
+        # an overflow (rows dropped) is detected and raised by the next forward / check_overflow()
+        env_f = __import__("os").environ.get("DCMOE_ROW_CAPACITY_FACTOR")
+        self.row_capacity_factor: Optional[float] = float(env_f) if env_f else None
         self.last_workspace: Optional[Workspace] = None
         self.stage_hook = None            # optional callable(stage_name) invoked between kernel launches (bench)
         self._reference_released = False
@@ -246,6 +248,14 @@ class DCMoE(nn.Module):
         dt = hidden_states.dtype
         if dt != self.gate.weight.dtype:
             raise TypeError(f"hidden_states dtype {dt} != parameter dtype {self.gate.weight.dtype}")
+        if hidden_states.device != self.gate.weight.device:
+            raise RuntimeError(f"hidden_states on {hidden_states.device} but the layer's parameters on {self.gate.weight.device}")
+        # launches go to the CURRENT device on the C side: make the input's device current (as PyTorch ops do)
+        with ops.on_device(hidden_states.device):
+            return self._forward(hidden_states, attention_mask, aux_balance_weight, router_logits, residual)
+
+    def _forward(self, hidden_states, attention_mask, aux_balance_weight, router_logits, residual):
+        dt = hidden_states.dtype
         if self.ep_size != 1:
             # expert parallelism configured the reference's way (config.ep_size, core.py:505-520): this rank holds
             # num_experts / ep_size routed experts and the forward runs ep.ExpertParallelDCMoE over the group set by
@@ -264,30 +274,44 @@ class DCMoE(nn.Module):
                                      f"({dist.get_world_size(group)})")
                 self._ep = ExpertParallelDCMoE(self, group)
             return self._ep(hidden_states, attention_mask, None)
+        self.pack_weights()
+        return self._forward_local(hidden_states, attention_mask, aux_balance_weight, router_logits, residual,
+                                   self._w13, self._w2)
+
+    def _forward_local(self, hidden_states, attention_mask, aux_balance_weight, router_logits, residual, w13, w2,
+                       before_ffn=None):
+        """The whole layer on this GPU with the packed weights ``w13`` / ``w2`` (all n_real + 1 groups).  ``before_ffn``
+        (weight-gather expert parallelism) is called after the permute launch and before the first GEMM launch: it
+        makes the stream wait for the staged weights."""
+        dt = hidden_states.dtype
         B, S, H = hidden_states.shape
         T = B * S
         x = hidden_states.reshape(T, H)
         if not x.is_contiguous():
             x = x.contiguous()
-        self.pack_weights()
-        ws = get_workspace(self.dims, dt, T, x.device, self.row_capacity)
+        ws = get_workspace(self.dims, dt, T, x.device, self.effective_row_capacity(T))
         self.last_workspace = ws
+        if ws.reduced:
+            ws.raise_if_overflowed()
         wg = self.gate.weight.detach()
         if not wg.is_contiguous():
             wg = wg.contiguous()
         hook = self.stage_hook or (lambda _name: None)
         out = torch.empty((B, S, H), dtype=dt, device=x.device)
-        if self.stage_hook is None and router_logits is None and T > 0 and (self.use_front_small or T > 64 or dt != torch.bfloat16):
+        res = None
+        if residual is not None:      # extension: fuse the decoder layer's residual add (model.py:242)
+            if residual.shape != hidden_states.shape or residual.dtype != dt:
+                raise ValueError("residual must match hidden_states in shape and dtype")
+            res = residual.reshape(T, H)
+            if not res.is_contiguous():
+                res = res.contiguous()
+        impl = self.ffn_impl if self.ffn_impl is not None else (0 if dt == torch.bfloat16 else 1)
+        if (self.stage_hook is None and before_ffn is None and router_logits is None and T > 0 and
+                (self.use_front_small or T > 64 or dt != torch.bfloat16)):
             # the common case: the whole layer in one host call (dcmoe_forward) -- same launches as below
-            res = None
-            if residual is not None:
-                if residual.shape != hidden_states.shape or residual.dtype != dt:
-                    raise ValueError("residual must match hidden_states in shape and dtype")
-                res = residual.reshape(T, H)
-                if not res.is_contiguous():
-                    res = res.contiguous()
-            impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
-            logits, top_k, mask, gw, aux = ops.forward(x, wg, self._w13, self._w2, ws, out, attention_mask, res, impl)
+            logits, top_k, mask, gw, aux = ops.forward(x, wg, w13, w2, ws, out, attention_mask, res, impl)
+            if ws.reduced and not torch.cuda.is_current_stream_capturing():
+                ws.note_overflow_async()
             if self.mlp_dynamic_top_p == 0:
                 top_k = top_k.to(torch.int32)
             return out, logits, top_k, mask, gw, aux
@@ -305,29 +329,43 @@ class DCMoE(nn.Module):
             if not small:
                 ops.permute(x, mask, gw, ws)
                 hook("permute")
-            impl = self.ffn_impl if self.ffn_impl is not None else (_DEFAULT_BF16_IMPL if dt == torch.bfloat16 else 1)
+            if before_ffn is not None:
+                before_ffn()
+                hook("wait_weights")
             if self.stage_hook is None:
-                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=0)     # both GEMMs, one call
+                ops.grouped_ffn(x, w13, w2, ws, impl, phase=0)     # both GEMMs, one call
             else:
-                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=1)
+                ops.grouped_ffn(x, w13, w2, ws, impl, phase=1)
                 hook("ffn_gemm1")
-                ops.grouped_ffn(x, self._w13, self._w2, ws, impl, phase=2)
+                ops.grouped_ffn(x, w13, w2, ws, impl, phase=2)
                 hook("ffn_gemm2")
-            res = None
-            if residual is not None:      # extension: fuse the decoder layer's residual add (model.py:242)
-                if residual.shape != hidden_states.shape or residual.dtype != dt:
-                    raise ValueError("residual must match hidden_states in shape and dtype")
-                res = residual.reshape(T, H)
-                if not res.is_contiguous():
-                    res = res.contiguous()
             aux = torch.empty((), dtype=torch.float32, device=x.device)
             ops.combine(ws, out, res, aux_out=aux)      # the 4-byte aux copy rides in the combine launch
             hook("combine")
         else:
             aux = ws.aux_loss.clone().reshape(())
+        if ws.reduced and not torch.cuda.is_current_stream_capturing():
+            ws.note_overflow_async()
         if self.mlp_dynamic_top_p == 0:
             top_k = top_k.to(torch.int32)        # the reference builds it with torch.full(..., dtype=torch.int) (core.py:257)
         return out, logits, top_k, mask, gw, aux
+
+    def effective_row_capacity(self, T: int) -> int:
+        """Rows of the FFN workspace for a T-token call: ``row_capacity`` if set, else from ``row_capacity_factor``
+        (0 = the worst case, which can never overflow)."""
+        if self.row_capacity:
+            return int(self.row_capacity)
+        f = self.row_capacity_factor
+        if f is None or f >= self.dims.n_real or T <= 64:
+            return 0
+        t_pad = (T + 127) // 128 * 128
+        routed = int(-(-f * T // 1))
+        return t_pad + (routed + 127) // 128 * 128 + 128 * self.dims.n_real
+
+    def check_overflow(self):
+        """Block until the last forward's overflow flag is on the host and raise if rows were dropped."""
+        if self.last_workspace is not None and self.last_workspace.reduced:
+            self.last_workspace.raise_if_overflowed(block=True)
 
 
 class PostAttentionMoE(nn.Module):
@@ -372,8 +410,9 @@ class PostAttentionMoE(nn.Module):
         w = self.post_attention_layernorm.weight.detach()
         if w.dtype != x.dtype:
             raise TypeError(f"hidden_states dtype {x.dtype} != norm weight dtype {w.dtype}")
-        normed = ops.rmsnorm(x, w, self.post_attention_layernorm.variance_epsilon, self.mlp.dims)
-        return self.mlp(normed, padding_token_mask, aux_balance_weight, residual=x)
+        with ops.on_device(x.device):
+            normed = ops.rmsnorm(x, w, self.post_attention_layernorm.variance_epsilon, self.mlp.dims)
+            return self.mlp(normed, padding_token_mask, aux_balance_weight, residual=x)
 
 
 # The reference's class name, so `utils.UniMoE_Audio_model.UniMoEAudioSparseMoeBlock = ...` reads naturally.

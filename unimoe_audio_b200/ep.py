@@ -1,24 +1,36 @@
 """Expert-parallel DCMoE (reference: AudioMOELayer.forward with an ep_group, core.py:446-493; group wiring
 core.py:505-520).
 
-One process per GPU.  Rank r owns routed experts [r*n_loc, (r+1)*n_loc) (core.py:505), the gate and the shared
-experts are replicated, every rank routes its own tokens.  Per forward and per rank:
+One process per GPU.  Rank r owns routed experts [r*n_loc, (r+1)*n_loc) (core.py:505), the gate and the shared experts
+are replicated, every rank routes its own tokens.  Three paths, picked per call from the local token count T (every
+rank of the group must call in lockstep with token counts on the same side of the two thresholds):
 
-    router -> local plan -> all-gather of (counts, T)  [NCCL, 36 bytes per rank]
-           -> ep_plan -> ep_dispatch (rows stored straight into the owners' packed buffers over NVLink)
-           -> barrier -> grouped FFN on the rows this rank owns (tcgen05) -> barrier
-           -> ep_combine (routed rows gathered from the owners' y buffers over NVLink + local shared row)
+  decode    world * T <= 64 (the same T on every rank): the tokens are replicated (pushed into every rank's buffer
+            over NVLink), routed identically everywhere, each rank streams only ITS experts' weights, and the combine
+            gathers each token's routed rows from their owners' y.
+  dispatch  the reference's exchange, un-padded: the permute kernel stores each selected row straight into the owner's
+            packed buffer over NVLink (``ep_dispatch``), the owners run the grouped FFN on the rows they received, the
+            combine kernel gathers the routed rows back with peer loads.
+  gather    T >= gather_min_tokens: every token row that travels costs 2 x 4 KB (there and back) while the remote
+            experts' weights are a fixed (world-1)/world x 270 MB per layer, so above ~9k tokens per rank it is the
+            WEIGHTS that should travel: each rank pulls the remote experts' packs into a staging pack with copy-engine
+            peer copies (no SM involved, double buffered so the fetch of call i+1 runs under the GEMMs of call i) and
+            runs the single-GPU forward on its own tokens.  No dispatch, no combine exchange, no collective at all,
+            and no load imbalance when the routing is skewed.  The experts stay sharded in HBM.
 
-Buffers touched by peers (x_packed, y, row_scale) are allocated with ``dcmoe_ipc_alloc`` and mapped into
-every rank with cudaIpc handles exchanged once per workspace.  ``LocalRanks`` runs the same kernels for R
-virtual ranks inside one process on one GPU (peer pointers are then ordinary local pointers); it is what the
-single-GPU tests use, as separate processes spinning on one GPU is not allowed on the test boxes.
+All cross-GPU synchronisation of the decode and dispatch paths is done through peer memory (``dcmoe_ep_barrier``:
+release/acquire flags, optionally carrying the counts / token rows as a payload); NCCL is only used for the one-off
+exchange of cudaIpc handles (``DCMOE_EP_FLAGS=0`` falls back to NCCL collectives).  Buffers touched by peers are
+allocated with ``dcmoe_ipc_alloc`` ONCE per (group, device, dtype, layer dims) -- sized for ``max_tokens`` tokens per
+rank -- and shared by all layers.  ``LocalRanks`` runs the same kernels for R virtual ranks inside one process on one
+GPU (peer pointers are then ordinary local pointers); it is what the single-GPU tests use.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import replace
-from typing import List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -27,6 +39,8 @@ from .dcmoe import DCMoE
 from .ops import LayerDims, Workspace
 
 EP_META_INTS = 32
+FLAG_SLOTS, MAX_RANKS = 8, 8
+SLOT_COUNTS, SLOT_DISPATCH, SLOT_FFN, SLOT_DECODE_X, SLOT_DECODE_Y = 0, 1, 2, 3, 4
 
 
 def ep_layout(all_counts: Sequence[Sequence[int]], rank: int, n_real: int):
@@ -53,6 +67,17 @@ def ep_layout(all_counts: Sequence[Sequence[int]], rank: int, n_real: int):
     return dest_base, dest_tpad, seg, [total[rank * n_loc + l] for l in range(n_loc)]
 
 
+def choose_path(T: int, world: int, dtype, mode: str = "auto", gather_min_tokens: int = 8192, decode_ok: bool = True) -> str:
+    """Which expert-parallel path a call with T local tokens takes (host logic, also used by the CPU tests)."""
+    if T <= 0:
+        return "dispatch"
+    if decode_ok and dtype == torch.bfloat16 and T * world <= 64:
+        return "decode"
+    if mode == "gather" or (mode == "auto" and T >= gather_min_tokens):
+        return "gather"
+    return "dispatch"
+
+
 class _RawCuda:
     def __init__(self, ptr: int, nbytes: int):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -62,43 +87,257 @@ def _wrap(ptr: int, nbytes: int, dtype, shape, device) -> torch.Tensor:
     return torch.as_tensor(_RawCuda(ptr, nbytes), device=device).view(dtype).view(shape)
 
 
-class EpWorkspace(Workspace):
-    """Workspace whose peer-visible buffers come from dcmoe_ipc_alloc (exportable with cudaIpcGetMemHandle)."""
+def _ptr_array(values: Sequence[int]):
+    return (ctypes.c_void_p * len(values))(*values)
 
-    def __init__(self, dims: LayerDims, dtype, T: int, device, row_capacity: int, ipc: bool):
-        super().__init__(dims, dtype, T, device, row_capacity, alloc_peer_visible=not ipc)
+
+class IpcBuffer:
+    """Device memory from ``dcmoe_ipc_alloc`` (plain cudaMalloc: exportable with cudaIpcGetMemHandle, unlike a slice of
+    the caching allocator's blocks).  ``ipc=False`` (virtual ranks, one process) uses the caching allocator."""
+
+    def __init__(self, nbytes: int, device, ipc: bool, zero: bool = False):
+        self.nbytes, self.device, self.ipc = int(nbytes), torch.device(device), ipc
+        self._torch = None
+        if ipc:
+            p = ctypes.c_void_p()
+            with ops.on_device(self.device):
+                _lib.check(_lib.load().dcmoe_ipc_alloc(self.nbytes, ctypes.byref(p)), "dcmoe_ipc_alloc")
+            self.ptr = p.value
+        else:
+            self._torch = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            self.ptr = self._torch.data_ptr()
+        if zero:
+            self.view(torch.uint8, (self.nbytes,)).zero_()
+
+    def view(self, dtype, shape) -> torch.Tensor:
+        return _wrap(self.ptr, self.nbytes, dtype, shape, self.device)
+
+    def export(self) -> bytes:
+        buf = (ctypes.c_uint8 * 64)()
+        _lib.check(_lib.load().dcmoe_ipc_export(self.ptr, buf), "dcmoe_ipc_export")
+        return bytes(buf)
+
+    def free(self):
+        if self.ipc and self.ptr:
+            try:
+                _lib.load().dcmoe_ipc_free(self.ptr)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+        self.ptr = 0
+        self._torch = None
+
+
+class EpWorkspace(Workspace):
+    """Workspace whose peer-visible buffers (x_packed, y, row_scale) come from ``IpcBuffer``; it also owns the fp32
+    partial sums of the overlapped combine, so that everything sized by T is rebuilt together."""
+
+    def __init__(self, dims: LayerDims, dtype, T: int, device, row_capacity: int, ipc: bool, shared: Optional[dict] = None):
+        super().__init__(dims, dtype, T, device, row_capacity, alloc_peer_visible=False)
         self.ep_meta = torch.zeros(EP_META_INTS, dtype=torch.int32, device=self.device)
         self.ipc = ipc
-        self._raw = {}
-        if ipc:
-            lib = _lib.load()
-            es = torch.empty((), dtype=dtype).element_size()
-            with torch.cuda.device(self.device):
-                for name, dt, esz in (("x_packed", dtype, es), ("y", dtype, es), ("row_scale", torch.float32, 4)):
-                    shape = self.shapes[name]
-                    nbytes = shape[0] * shape[1] * esz
-                    p = ctypes.c_void_p()
-                    _lib.check(lib.dcmoe_ipc_alloc(nbytes, ctypes.byref(p)), "dcmoe_ipc_alloc")
-                    self._raw[name] = (p.value, nbytes)
-                    setattr(self, name, _wrap(p.value, nbytes, dt, shape, self.device))
-            self.row_scale.zero_()
+        es = torch.empty((), dtype=dtype).element_size()
+        self._bufs: Dict[str, IpcBuffer] = {}
+        for name, dt, esz in (("x_packed", dtype, es), ("y", dtype, es), ("row_scale", torch.float32, 4)):
+            shape = self.shapes[name]
+            if shared is not None and name in shared:       # views of buffers a larger workspace owns
+                buf = shared[name]
+                assert shape[0] * shape[1] * esz <= buf.nbytes
+            else:
+                buf = IpcBuffer(shape[0] * shape[1] * esz, self.device, ipc)
+                self._bufs[name] = buf
+            setattr(self, name, _wrap(buf.ptr, shape[0] * shape[1] * esz, dt, shape, self.device))
+        self.row_scale.zero_()
+        self.partial = torch.empty((max(T, 1), dims.hidden_size), dtype=torch.float32, device=self.device)
 
-    def export_handles(self) -> dict:
-        lib = _lib.load()
-        out = {}
-        for name, (ptr, _n) in self._raw.items():
-            buf = (ctypes.c_uint8 * 64)()
-            _lib.check(lib.dcmoe_ipc_export(ptr, buf), "dcmoe_ipc_export")
-            out[name] = bytes(buf)
-        return out
+    def buffers(self) -> Dict[str, IpcBuffer]:
+        return self._bufs
+
+    def free(self):
+        for b in self._bufs.values():
+            b.free()
+        self._bufs = {}
 
     def __del__(self):  # pragma: no cover - best effort
-        try:
-            lib = _lib.load()
-            for ptr, _n in self._raw.values():
-                lib.dcmoe_ipc_free(ptr)
-        except Exception:  # noqa: BLE001
-            pass
+        self.free()
+
+
+class EpContext:
+    """What the layers of one model share per (expert-parallel group, device, dtype, layer dims): the peer-visible
+    workspace of the dispatch path, the decode path's buffers, the flag array of the peer-memory barriers, the staging
+    packs of the weight-gather path and the cudaIpc mappings of all of them.  Built collectively (every rank of the group
+    at the same call); nothing in it is re-exchanged afterwards."""
+
+    _registry: Dict[tuple, "EpContext"] = {}
+
+    @classmethod
+    def get(cls, group, rank: int, world: int, dims: LayerDims, dtype, device) -> "EpContext":
+        key = (id(group) if group is not None else None, rank, world, dims, dtype, torch.device(device))
+        ctx = cls._registry.get(key) if group is not None else None
+        if ctx is None:
+            ctx = cls(group, rank, world, dims, dtype, device)
+            if group is not None:
+                cls._registry[key] = ctx
+        return ctx
+
+    def __init__(self, group, rank: int, world: int, dims: LayerDims, dtype, device):
+        self.group, self.rank, self.world = group, rank, world
+        self.dims, self.dtype, self.device = dims, dtype, torch.device(device)
+        self.n_loc = dims.n_real // world
+        self.real = group is not None                  # separate processes (cudaIpc) vs virtual ranks in one process
+        self.use_flags = os.environ.get("DCMOE_EP_FLAGS", "1") != "0"
+        self._imported: List[int] = []
+        # ---- dispatch path ----
+        self.max_tokens = 0
+        self.ws_full: Optional[EpWorkspace] = None     # owns the peer-visible buffers, sized for max_tokens per rank
+        self.ws_by_T: Dict[int, EpWorkspace] = {}
+        self.peer = None                               # (x_packed, row_scale, y) pointer arrays over the ranks
+        self.counts_table: Optional[IpcBuffer] = None  # [world][n_real + 1] int32, filled by the peers (barrier payload)
+        self.peer_counts = None
+        # ---- flags ----
+        self.flags: Optional[IpcBuffer] = None
+        self.peer_flags = None
+        self.epoch = [0] * FLAG_SLOTS
+        self._nccl_flag = None
+        # ---- decode path ----
+        self.dy: Optional[IpcBuffer] = None            # y of the decode-sized path, for 64 tokens
+        self.dx: Optional[IpcBuffer] = None            # gathered token rows x_all (and their padding masks) for 64 tokens
+        self.dpeer_y = self.dpeer_x = None
+        self.dws_by_T: Dict[int, EpWorkspace] = {}
+        # ---- weight-gather path ----
+        self.stage = None                              # [(w13_full, w2_full)] x 2 slots
+        self.slot_ready = self.slot_free = None
+        self.copy_stream = None
+        self.n_fetch = 0
+
+    # ------------------------------------------------------------------ handle exchange (collective, one-off)
+    def _exchange(self, bufs: Dict[str, IpcBuffer]) -> Dict[str, List[int]]:
+        """All-gather the cudaIpc handles of ``bufs`` over the group and map the peers' buffers.  Collective."""
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        mine = {k: b.export() for k, b in bufs.items()}
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        ptrs = {k: [] for k in bufs}
+        with ops.on_device(self.device):
+            for r in range(self.world):
+                for name in bufs:
+                    if r == self.rank:
+                        ptrs[name].append(bufs[name].ptr)
+                    else:
+                        p = ctypes.c_void_p()
+                        hb = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r][name])
+                        _lib.check(lib.dcmoe_ipc_import(hb, ctypes.byref(p)), "dcmoe_ipc_import")
+                        self._imported.append(p.value)
+                        ptrs[name].append(p.value)
+        return ptrs
+
+    def _ensure_flags(self):
+        if self.flags is not None or not self.real:
+            return
+        self.flags = IpcBuffer(FLAG_SLOTS * MAX_RANKS * 4, self.device, True, zero=True)
+        self.counts_table = IpcBuffer(2 * MAX_RANKS * 16 * 4, self.device, True, zero=True)   # two call parities
+        torch.cuda.synchronize(self.device)
+        ptrs = self._exchange({"flags": self.flags, "counts": self.counts_table})
+        self.peer_flags = _ptr_array(ptrs["flags"])
+        self._peer_counts_raw = ptrs["counts"]
+        self._nccl_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def barrier(self, slot: int, payload: Optional[torch.Tensor] = None, peer_dst=None):
+        """Stream-ordered barrier of the group on the current stream; with ``payload`` also an all-gather of it into the
+        buffers ``peer_dst`` points to (rank q's payload at offset q * payload bytes)."""
+        import torch.distributed as dist
+
+        if not self.real:
+            return
+        if not self.use_flags:
+            assert payload is None
+            dist.all_reduce(self._nccl_flag, group=self.group)
+            return
+        self.epoch[slot] += 1
+        nbytes = 0 if payload is None else payload.numel() * payload.element_size()
+        _lib.check(_lib.load().dcmoe_ep_barrier(self.peer_flags, self.rank, self.world, slot, self.epoch[slot],
+                                                None if payload is None else payload.data_ptr(), nbytes, peer_dst,
+                                                torch.cuda.current_stream(self.device).cuda_stream), "dcmoe_ep_barrier")
+
+    # ------------------------------------------------------------------ dispatch path
+    def row_capacity_for(self, T: int, T_global_max: int) -> int:
+        t_pad = (T + 127) // 128 * 128
+        return t_pad + self.n_loc * T_global_max + 128 * self.n_loc
+
+    def configure_dispatch(self, max_tokens: int):
+        """Allocate (once) the peer-visible dispatch workspace for up to ``max_tokens`` tokens PER RANK and exchange its
+        handles.  Collective.  Worst case: every token of every rank selects every expert of one owner."""
+        import torch.distributed as dist
+
+        if self.ws_full is not None:
+            # growing means freeing buffers peers may still be reading: everyone arrives here first
+            torch.cuda.synchronize(self.device)
+            if self.real:
+                dist.barrier(group=self.group)
+            self.close_dispatch()
+        self.max_tokens = int(max_tokens)
+        cap = self.row_capacity_for(self.max_tokens, self.max_tokens * self.world)
+        self.ws_full = EpWorkspace(self.dims, self.dtype, self.max_tokens, self.device, cap, self.real)
+        self.ws_by_T = {self.max_tokens: self.ws_full}
+        if self.real:
+            self._ensure_flags()
+            torch.cuda.synchronize(self.device)
+            ptrs = self._exchange(self.ws_full.buffers())
+            self.peer = (_ptr_array(ptrs["x_packed"]), _ptr_array(ptrs["row_scale"]), _ptr_array(ptrs["y"]))
+
+    def dispatch_workspace(self, T: int) -> EpWorkspace:
+        """Workspace of a T-token dispatch call: plan / h / maps sized for T, peer-visible buffers = views of the
+        max_tokens workspace (same base addresses on every rank whatever T is)."""
+        ws = self.ws_by_T.get(T)
+        if ws is None:
+            if len(self.ws_by_T) >= 6:
+                for k in list(self.ws_by_T):
+                    if k != self.max_tokens:
+                        self.ws_by_T.pop(k)
+                        break
+            cap = self.row_capacity_for(T, self.max_tokens * self.world)
+            ws = EpWorkspace(self.dims, self.dtype, T, self.device, cap, self.real, shared=self.ws_full.buffers()
+                             if self.real else None)
+            self.ws_by_T[T] = ws
+        return ws
+
+    def close_dispatch(self):
+        for ws in self.ws_by_T.values():
+            ws.free()
+        self.ws_by_T, self.ws_full, self.peer = {}, None, None
+
+    # ------------------------------------------------------------------ weight-gather path
+    def ensure_staging(self):
+        if self.stage is not None:
+            return
+        d = self.dims
+        G = d.n_real + 1
+        mk = lambda: (torch.empty((G, 2 * d.dynamic_intermediate_size, d.hidden_size), dtype=self.dtype, device=self.device),  # noqa: E731
+                      torch.empty((G, d.hidden_size, d.dynamic_intermediate_size), dtype=self.dtype, device=self.device))
+        self.stage = [mk(), mk()]
+        self.slot_ready = [torch.cuda.Event() for _ in range(2)]
+        self.slot_free = [torch.cuda.Event() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's.  Call on every rank after a barrier (nobody may still be
+        reading); process exit does the same implicitly."""
+        lib = _lib.load()
+        for p in self._imported:
+            try:
+                lib.dcmoe_ipc_close(p)
+            except Exception:  # noqa: BLE001
+                pass
+        self._imported = []
+        self.close_dispatch()
+        for b in (self.flags, self.counts_table, self.dy, self.dx):
+            if b is not None:
+                b.free()
+        self.flags = self.counts_table = self.dy = self.dx = None
+        for k, v in list(EpContext._registry.items()):
+            if v is self:
+                EpContext._registry.pop(k)
 
 
 class ExpertParallelDCMoE:
@@ -115,58 +354,68 @@ class ExpertParallelDCMoE:
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         d = module.dims
-        if d.n_real % self.world != 0 or self.world > 8:
+        if d.n_real % self.world != 0 or self.world > MAX_RANKS:
             raise ValueError(f"num_experts ({d.n_real}) must be divisible by ep_size ({self.world}) (core.py:505), ep_size <= 8")
         self.n_loc = d.n_real // self.world
         self.local_dims = replace(d, n_real=self.n_loc)
         self._w13 = self._w2 = None
+        self._wbuf: Optional[Dict[str, IpcBuffer]] = None
+        self._peer_w = None                # (w13, w2) pointer arrays over the ranks (weight-gather path)
+        self.ctx: Optional[EpContext] = None
         self.ws: Optional[EpWorkspace] = None
-        self._peer = None
-        self._imported = []
-        self._flag = None
-        self.kernels_per_step = 11  # router, plan, ep_plan, shared scales, dispatch, 4 x ffn gemm, combine x 2
-        self.row_capacity = 0
-        import os
-        self.overlap = os.environ.get("DCMOE_EP_OVERLAP", "1") != "0"   # comm stream under the shared experts' GEMMs
+        self.mode = os.environ.get("DCMOE_EP_MODE", "auto")                      # auto | dispatch | gather
+        self.gather_min_tokens = int(os.environ.get("DCMOE_EP_GATHER_MIN_TOKENS", "8192"))
+        self.check_lockstep = os.environ.get("DCMOE_EP_CHECK", "0") == "1"       # debug: host all-gather of T per call
+        self.overlap = os.environ.get("DCMOE_EP_OVERLAP", "1") != "0"   # dispatch path: comm stream under the shared experts' GEMMs
         self.comm_ctas = int(os.environ.get("DCMOE_EP_COMM_CTAS", "148"))   # grid cap of dispatch / partial combine (0 = full)
         self.gemm_ctas = int(os.environ.get("DCMOE_EP_GEMM_CTAS", "0"))   # CTAs of the shared GEMMs that run under comm (0 = all SMs)
-        # eighths of the shared experts' GEMM-1 that run under the dispatch, the rest then runs with GEMM-2 under the
-        # combine gather; 0 = all of it under the dispatch.  Measured at 8 GPUs with 4/8: no gain (5.19 vs 4.86 ms per
-        # step) -- the gather and the GEMMs compete for the same SMs and HBM, the gather just stretches from 0.70 to
-        # 1.15 ms -- so the split stays off by default
-        self.shared_split = int(os.environ.get("DCMOE_EP_SHARED_SPLIT", "0"))
         self._side = None
-        self.comm_events = []        # (name, start, end) CUDA events of the comm-stream kernels, filled when a stage hook is set
+        self.comm_events = []        # (name, start, end) CUDA events of the comm / copy streams, filled when a stage hook is set
         self._local_cfg = None
-        self._partial = None
-        # decode-sized calls (world * T <= 64 tokens, the same T on every rank): replicated routing of the gathered tokens,
-        # local experts' rows computed by the weight-streaming kernels, combine over peer memory (see decode_forward)
         self.decode_mode = os.environ.get("DCMOE_EP_DECODE", "1") != "0"
         self._dws: Optional[EpWorkspace] = None
-        self._dws_by_T = {}
-        self._dy_raw = None               # (ptr, bytes) of the peer-visible y of the decode-sized path
-        self._dpeer = None
-        self._dflag = None
+        self.last_path = None
+        self._call = 0
 
-    # ------------------------------------------------------------------ setup
+    @property
+    def kernels_per_step(self) -> int:
+        """Kernels of this package launched per forward on the path taken last (bench.py's gpu_launches)."""
+        return {"gather": 6, "decode": 6, "dispatch": 14 if self.overlap else 11}.get(self.last_path or "dispatch", 11)
+
+    def context(self, dtype, device) -> EpContext:
+        if self.ctx is None or self.ctx.dtype != dtype or self.ctx.device != torch.device(device):
+            self.ctx = EpContext.get(self.group, self.rank, self.world, self.m.dims, dtype, device)
+        return self.ctx
+
+    # ------------------------------------------------------------------ weights
+    def _alloc_local_packs(self, dtype, device):
+        d = self.m.dims
+        G = self.n_loc + 1
+        es = torch.empty((), dtype=dtype).element_size()
+        n13 = G * 2 * d.dynamic_intermediate_size * d.hidden_size * es
+        n2 = G * d.hidden_size * d.dynamic_intermediate_size * es
+        ipc = self.group is not None
+        self._wbuf = {"w13": IpcBuffer(n13, device, ipc), "w2": IpcBuffer(n2, device, ipc)}
+        self._w13 = self._wbuf["w13"].view(dtype, (G, 2 * d.dynamic_intermediate_size, d.hidden_size))
+        self._w2 = self._wbuf["w2"].view(dtype, (G, d.hidden_size, d.dynamic_intermediate_size))
+
     def pack_local_weights(self):
+        """This rank's packs: its n_loc routed experts as groups 0..n_loc-1, the shared pair as group n_loc.  They live in
+        cudaIpc-exportable memory so that the peers can pull them (weight-gather path)."""
         if self._w13 is not None:
             return
         m, d, ld = self.m, self.m.dims, self.local_dims
         p = m.gate.weight
-        G = self.n_loc + 1
-        w13 = torch.empty((G, 2 * d.dynamic_intermediate_size, d.hidden_size), dtype=p.dtype, device=p.device)
-        w2 = torch.empty((G, d.hidden_size, d.dynamic_intermediate_size), dtype=p.dtype, device=p.device)
+        self._alloc_local_packs(p.dtype, p.device)
         routed, shared = m._expert_params()
         for l in range(self.n_loc):
             e = self.rank * self.n_loc + l
             ex = routed[e] if len(routed) == d.n_real else routed[l]   # full module or local-experts-only module
             ops.pack_expert(ex.gate_proj.weight.detach().contiguous(), ex.up_proj.weight.detach().contiguous(),
-                            ex.down_proj.weight.detach().contiguous(), l, 0, ld, w13, w2)
+                            ex.down_proj.weight.detach().contiguous(), l, 0, ld, self._w13, self._w2)
         for i, ex in enumerate(shared):
             ops.pack_expert(ex.gate_proj.weight.detach().contiguous(), ex.up_proj.weight.detach().contiguous(),
-                            ex.down_proj.weight.detach().contiguous(), self.n_loc, i, ld, w13, w2)
-        self._w13, self._w2 = w13, w2
+                            ex.down_proj.weight.detach().contiguous(), self.n_loc, i, ld, self._w13, self._w2)
 
     def set_packed_local_weights(self, w13: torch.Tensor, w2: torch.Tensor):
         """Use packs built elsewhere (``checkpoint.load_dcmoe_ep``: this rank's experts read straight from a
@@ -175,46 +424,25 @@ class ExpertParallelDCMoE:
         if tuple(w13.shape) != (G, 2 * d.dynamic_intermediate_size, d.hidden_size) or \
                 tuple(w2.shape) != (G, d.hidden_size, d.dynamic_intermediate_size) or not (w13.is_cuda and w2.is_cuda):
             raise ValueError("packed local weights have the wrong shape for this rank's expert count")
-        self._w13, self._w2 = w13.contiguous(), w2.contiguous()
+        self._alloc_local_packs(w13.dtype, w13.device)
+        self._w13.copy_(w13)
+        self._w2.copy_(w2)
+        self._peer_w = None
 
-    def default_row_capacity(self, T: int, T_global: int) -> int:
-        t_pad = (T + 127) // 128 * 128
-        return t_pad + self.n_loc * T_global + 128 * self.n_loc
+    def set_peer_weights(self, w13: List[int], w2: List[int]):
+        self._peer_w = (_ptr_array(w13), _ptr_array(w2))
 
-    def ensure_workspace(self, T: int, dtype, device, ipc: bool, T_global: Optional[int] = None) -> EpWorkspace:
-        cap = self.row_capacity or self.default_row_capacity(T, T_global if T_global is not None else T * self.world)
-        if self.ws is None or self.ws.T != T or self.ws.dtype != dtype or self.ws.row_capacity != cap:
-            self.ws = EpWorkspace(self.m.dims, dtype, T, device, cap, ipc)
-            self._peer = None
-        self.m.last_workspace = self.ws
-        return self.ws
-
-    def set_peers(self, x_packed: List[int], row_scale: List[int], y: List[int]):
-        arr = lambda v: (ctypes.c_void_p * len(v))(*v)  # noqa: E731
-        self._peer = (arr(x_packed), arr(row_scale), arr(y))
-
-    def _exchange_handles(self):
+    def _exchange_weight_handles(self):
+        """Collective, once per layer: map every rank's packs.  The barrier makes sure they are packed."""
         import torch.distributed as dist
 
-        lib = _lib.load()
-        mine = self.ws.export_handles()
-        allh = [None] * self.world
-        dist.all_gather_object(allh, mine, group=self.group)
-        ptrs = {"x_packed": [], "row_scale": [], "y": []}
-        for r in range(self.world):
-            for name in ptrs:
-                if r == self.rank:
-                    ptrs[name].append(self.ws._raw[name][0])
-                else:
-                    p = ctypes.c_void_p()
-                    buf = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r][name])
-                    _lib.check(lib.dcmoe_ipc_import(buf, ctypes.byref(p)), "dcmoe_ipc_import")
-                    self._imported.append(p.value)
-                    ptrs[name].append(p.value)
-        self.set_peers(ptrs["x_packed"], ptrs["row_scale"], ptrs["y"])
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.ws.device)
+        ctx = self.ctx
+        torch.cuda.synchronize(ctx.device)
+        ptrs = ctx._exchange(self._wbuf)
+        dist.barrier(group=self.group)
+        self.set_peer_weights(ptrs["w13"], ptrs["w2"])
 
-    # ------------------------------------------------------------------ phases (all launch-only)
+    # ------------------------------------------------------------------ dispatch path: phases (all launch-only)
     def phase_route(self, x: torch.Tensor, attention_mask=None, router_logits=None):
         m, ws = self.m, self.ws
         hook = m.stage_hook or (lambda _n: None)
@@ -239,7 +467,7 @@ class ExpertParallelDCMoE:
         ws = self.ws
         hook = self.m.stage_hook or (lambda _n: None)
         st = torch.cuda.current_stream().cuda_stream
-        self._all_counts = all_counts.contiguous()
+        self._all_counts = all_counts
         _, _, _mask, gw = self._route
         _lib.check(lib.dcmoe_ep_plan(self._all_counts.data_ptr(), self.rank, self.world, ws.T, ws.row_capacity, ws.cfg,
                                      ws.plan.data_ptr(), ws.ep_meta.data_ptr(), gw.data_ptr(), ws.row_scale.data_ptr(), st),
@@ -256,21 +484,18 @@ class ExpertParallelDCMoE:
                                          ws.plan.data_ptr(), ws.ep_meta.data_ptr(), self.rank, self.world, xp, rs,
                                          ws.slot_of.data_ptr(), max_ctas, st), "dcmoe_ep_dispatch")
 
-    def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0,
-                  shared_split: int = 0):
-        """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2/3 = all / shared-expert / routed row tiles / the shared
-        tiles from the split point on; shared_split s (1..7): split point at s/8 of the shared tiles (group 1 stops there)."""
+    def phase_ffn(self, phase: int = 0, group_sel: int = 0, name: Optional[str] = None, max_ctas: int = 0):
+        """phase 0/1/2 = both / GEMM-1 / GEMM-2; group_sel 0/1/2 = all / shared-expert / routed row tiles."""
         lib = _lib.load()
         ws = self.ws
         if self._local_cfg is None:
             self._local_cfg = self.local_dims.c_config(ws.dtype)
-        from .dcmoe import _DEFAULT_BF16_IMPL
-        impl = self.m.ffn_impl if self.m.ffn_impl is not None else (_DEFAULT_BF16_IMPL if ws.dtype == torch.bfloat16 else 1)
+        impl = self.m.ffn_impl if self.m.ffn_impl is not None else (0 if ws.dtype == torch.bfloat16 else 1)
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.dcmoe_grouped_ffn(self._x.data_ptr(), ws.x_packed.data_ptr(), self._w13.data_ptr(),
                                          self._w2.data_ptr(), ws.row_scale.data_ptr(), ws.T, ws.row_capacity, self._local_cfg,
                                          ws.plan.data_ptr(), ws.h.data_ptr(), ws.y.data_ptr(), impl,
-                                         phase | (group_sel << 4) | (max_ctas << 8) | (1 << 20) | (shared_split << 28), st),
+                                         phase | (group_sel << 4) | (max_ctas << 8) | (1 << 20), st),
                    "dcmoe_grouped_ffn")
         if name and self.m.stage_hook:
             self.m.stage_hook(name)
@@ -279,12 +504,13 @@ class ExpertParallelDCMoE:
         lib = _lib.load()
         ws = self.ws
         _xp, _rs, y = self._peer
-        if mode != 0 and self._partial is None:
-            self._partial = torch.empty((max(ws.T, 1), self.m.dims.hidden_size), dtype=torch.float32, device=ws.device)
         _lib.check(lib.dcmoe_ep_combine(ws.y.data_ptr(), y, ws.slot_of.data_ptr(), ws.T, ws.cfg, self.world, mode,
-                                        None if self._partial is None else self._partial.data_ptr(),
+                                        ws.partial.data_ptr() if mode != 0 else None,
                                         None if out is None else out.data_ptr(), max_ctas,
                                         torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
+
+    def set_peers(self, x_packed: List[int], row_scale: List[int], y: List[int]):
+        self._peer = (_ptr_array(x_packed), _ptr_array(row_scale), _ptr_array(y))
 
     # ------------------------------------------------------------------ decode-sized calls
     def decode_applicable(self, T: int, dtype) -> bool:
@@ -293,54 +519,39 @@ class ExpertParallelDCMoE:
 
     def ensure_decode_workspace(self, T_total: int, device, ipc: bool) -> EpWorkspace:
         """Workspace of a decode-sized call on T_total gathered tokens (kept per token count).  Across processes the
-        only peer-visible buffer is y; it is allocated ONCE, for 64 tokens, and every per-T workspace views it, so the
-        cudaIpc handles are exchanged a single time however the batch size varies."""
-        ws = self._dws_by_T.get(T_total)
+        peer-visible buffers (y, and x_all which the peers fill) are allocated ONCE, for 64 tokens, and every per-T
+        workspace views them, so the cudaIpc handles are exchanged a single time however the batch size varies."""
+        ctx = self.context(torch.bfloat16, device)
+        ws = ctx.dws_by_T.get(T_total)
         if ws is None:
-            if len(self._dws_by_T) >= 8:
-                self._dws_by_T.pop(next(iter(self._dws_by_T)))
-            ws = EpWorkspace(self.m.dims, torch.bfloat16, T_total, device, 0, False)      # worst-case rows for T_total tokens
-            ws.x_all = torch.empty((T_total, self.m.dims.hidden_size), dtype=torch.bfloat16, device=device)
+            H = self.m.dims.hidden_size
+            if len(ctx.dws_by_T) >= 8:
+                ctx.dws_by_T.pop(next(iter(ctx.dws_by_T)))
+            if ipc and ctx.dy is None:
+                sizes, _ = ops.query_sizes(self.m.dims, torch.bfloat16, 64, 0)
+                ctx.dy = IpcBuffer(int(sizes.row_capacity) * H * 2, device, True)
+                ctx.dx = IpcBuffer(64 * H * 2 + 64 * 4, device, True, zero=True)   # rows, then int32 padding masks
+                ctx._ensure_flags()
+                torch.cuda.synchronize(ctx.device)
+                ptrs = ctx._exchange({"dy": ctx.dy, "dx": ctx.dx})
+                ctx.dpeer_y = _ptr_array(ptrs["dy"])
+                ctx.dpeer_x = _ptr_array(ptrs["dx"])
+                ctx.dpeer_am = _ptr_array([p + 64 * H * 2 for p in ptrs["dx"]])
+            ws = EpWorkspace(self.m.dims, torch.bfloat16, T_total, device, 0, False)   # worst-case rows for T_total tokens
             if ipc:
-                H = self.m.dims.hidden_size
-                if self._dy_raw is None:
-                    lib = _lib.load()
-                    sizes, _ = ops.query_sizes(self.m.dims, torch.bfloat16, 64, 0)
-                    nbytes = int(sizes.row_capacity) * H * 2
-                    p = ctypes.c_void_p()
-                    with torch.cuda.device(device):
-                        _lib.check(lib.dcmoe_ipc_alloc(nbytes, ctypes.byref(p)), "dcmoe_ipc_alloc")
-                    self._dy_raw = (p.value, nbytes)
-                assert ws.row_capacity * H * 2 <= self._dy_raw[1]
-                ws.y = _wrap(self._dy_raw[0], ws.row_capacity * H * 2, torch.bfloat16, (ws.row_capacity, H), ws.device)
+                ws.y = _wrap(ctx.dy.ptr, ws.row_capacity * H * 2, torch.bfloat16, (ws.row_capacity, H), ws.device)
+                ws.x_all = ctx.dx.view(torch.uint8, (ctx.dx.nbytes,))[: T_total * H * 2].view(torch.bfloat16).view(T_total, H)
+                ws.am_all = ctx.dx.view(torch.uint8, (ctx.dx.nbytes,))[64 * H * 2: 64 * H * 2 + T_total * 4].view(torch.int32)
                 ws._c_ws = None
-            self._dws_by_T[T_total] = ws
+            else:
+                ws.x_all = torch.empty((T_total, H), dtype=torch.bfloat16, device=device)
+                ws.am_all = torch.ones(T_total, dtype=torch.int32, device=device)
+            ctx.dws_by_T[T_total] = ws
         self._dws = ws
         return ws
 
     def set_decode_peers(self, y: List[int]):
-        self._dpeer = (ctypes.c_void_p * len(y))(*y)
-
-    def _exchange_decode_handles(self):
-        import torch.distributed as dist
-
-        lib = _lib.load()
-        buf = (ctypes.c_uint8 * 64)()
-        _lib.check(lib.dcmoe_ipc_export(self._dy_raw[0], buf), "dcmoe_ipc_export")
-        allh = [None] * self.world
-        dist.all_gather_object(allh, bytes(buf), group=self.group)
-        ys = []
-        for r in range(self.world):
-            if r == self.rank:
-                ys.append(self._dy_raw[0])
-            else:
-                p = ctypes.c_void_p()
-                hb = (ctypes.c_uint8 * 64).from_buffer_copy(allh[r])
-                _lib.check(lib.dcmoe_ipc_import(hb, ctypes.byref(p)), "dcmoe_ipc_import")
-                self._imported.append(p.value)
-                ys.append(p.value)
-        self.set_decode_peers(ys)
-        self._dflag = torch.zeros(1, dtype=torch.int32, device=self._dws.device)
+        self._dpeer = _ptr_array(y)
 
     def decode_route_and_ffn(self, attention_mask_all=None):
         """Replicated part of a decode-sized call, after x_all holds every rank's tokens (rank-major): fused front end
@@ -365,9 +576,9 @@ class ExpertParallelDCMoE:
                                         out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream), "dcmoe_ep_combine")
 
     def decode_forward(self, hidden_states: torch.Tensor, attention_mask=None):
-        """Expert parallelism for decode-sized calls.  The dispatch / combine exchange of the large-T path costs eleven
-        launches and three collectives (340 us per layer at T = 2); with a handful of tokens it is cheaper to replicate
-        the tokens (one all-gather of world * T rows) and the routing, let every rank stream only ITS experts' weights,
+        """Expert parallelism for decode-sized calls.  The dispatch / combine exchange of the large-T path costs a dozen
+        launches; with a handful of tokens it is cheaper to replicate the tokens (every rank pushes its rows into every
+        rank's x_all: one barrier-with-payload launch) and the routing, let every rank stream only ITS experts' weights,
         and gather the routed rows in the combine.  Same kernels and row space as a single-GPU call on the gathered
         tokens, so the output equals that call's bit for bit.  (aux_loss is then the loss over the gathered tokens.)"""
         import torch.distributed as dist
@@ -379,61 +590,171 @@ class ExpertParallelDCMoE:
             x = x.contiguous()
         self.pack_local_weights()
         ws = self.ensure_decode_workspace(T * self.world, x.device, ipc=True)
-        if self._dpeer is None:
-            self._exchange_decode_handles()
-        dist.all_gather_into_tensor(ws.x_all, x, group=self.group)     # also: every rank is done reading the previous y
+        ctx = self.ctx
+        self.set_decode_peers(list(ctx.dpeer_y))
         am_all = None
-        if attention_mask is not None:
-            am = attention_mask.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
-            am_all = torch.empty(T * self.world, dtype=torch.int32, device=x.device)
-            dist.all_gather_into_tensor(am_all, am, group=self.group)
+        if ctx.use_flags:
+            # "every rank is done reading the previous call's y / x_all" is implied: a rank only passes the y barrier
+            # of call i after every rank arrived there, i.e. after every rank's combine of call i-1 ... and the x push
+            # of call i+1 can only overwrite rows whose readers (front end of call i) precede that rank's y barrier
+            if attention_mask is not None:
+                am = attention_mask.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+                ctx.barrier(SLOT_DECODE_X, am, ctx.dpeer_am)
+                am_all = ws.am_all
+            ctx.barrier(SLOT_DECODE_X, x, ctx.dpeer_x)
+        else:
+            dist.all_gather_into_tensor(ws.x_all, x, group=self.group)
+            if attention_mask is not None:
+                am = attention_mask.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+                am_all = torch.empty(T * self.world, dtype=torch.int32, device=x.device)
+                dist.all_gather_into_tensor(am_all, am, group=self.group)
         self.decode_route_and_ffn(am_all)
-        dist.all_reduce(self._dflag, group=self.group)                 # every owner's y rows are complete
+        ctx.barrier(SLOT_DECODE_Y)                                     # every owner's y rows are complete
         out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
         self.decode_combine(T, out)
         logits, top_k, mask, gw = (t[self.rank * T:(self.rank + 1) * T] for t in self._droute)
         self.m.last_workspace = ws
         return out, logits, top_k, mask, gw, ws.aux_loss.clone().reshape(())
 
+    # ------------------------------------------------------------------ weight-gather path
+    def fetch_weights(self, slot: int):
+        """Enqueue, on the context's copy stream, the copies of every rank's packs into staging slot ``slot``."""
+        ctx = self.ctx
+        lib = _lib.load()
+        w13_full, w2_full = ctx.stage[slot]
+        cs = ctx.copy_stream
+        timed = self.m.stage_hook is not None
+        with torch.cuda.stream(cs):
+            cs.wait_event(ctx.slot_free[slot])          # the GEMMs that last read this slot are done
+            if timed:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(cs)
+            _lib.check(lib.dcmoe_ep_fetch_weights(self._peer_w[0], self._peer_w[1], self.rank, self.world,
+                                                  self.m.dims.c_config(ctx.dtype), w13_full.data_ptr(), w2_full.data_ptr(),
+                                                  cs.cuda_stream), "dcmoe_ep_fetch_weights")
+            if timed:
+                t1.record(cs)
+                self.comm_events.append(("weight_fetch", t0, t1))
+            ctx.slot_ready[slot].record(cs)
+
+    def gather_forward(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None):
+        """Weight-gather expert parallelism: pull every remote expert's packed weights over NVLink (copy engines) into a
+        staging pack, then run the single-GPU forward on this rank's tokens -- router, plan and permute run while the
+        copies are in flight; the staging packs are double buffered, so with the host running ahead the fetch of call
+        i+1 overlaps the GEMMs of call i.  Bit-equal to the single-GPU layer on the same rows (the FFN is row
+        independent); the aux loss is the loss over this rank's tokens, as on the dispatch path."""
+        ctx = self.context(hidden_states.dtype, hidden_states.device)
+        self.pack_local_weights()
+        if self._peer_w is None:
+            self._exchange_weight_handles()
+        ctx.ensure_staging()
+        slot = ctx.n_fetch & 1
+        ctx.n_fetch += 1
+        main = torch.cuda.current_stream(ctx.device)
+        self.fetch_weights(slot)
+        w13_full, w2_full = ctx.stage[slot]
+        out = self.m._forward_local(hidden_states, attention_mask, aux_balance_weight, None, None, w13_full, w2_full,
+                                    before_ffn=lambda: main.wait_event(ctx.slot_ready[slot]))
+        ctx.slot_free[slot].record(main)
+        return out
+
     # ------------------------------------------------------------------ distributed forward
-    @torch.no_grad()
-    def __call__(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
+    def _check_lockstep(self, T: int, path: str):
         import torch.distributed as dist
 
-        if aux_balance_weight is not None:
-            raise NotImplementedError("aux_balance_weight is training-only")
+        got = [None] * self.world
+        dist.all_gather_object(got, (T, path), group=self.group)
+        if len({p for _t, p in got}) != 1 or (path == "decode" and len({t for t, _p in got}) != 1):
+            raise RuntimeError(f"expert-parallel ranks diverged: (token count, path) per rank = {got}; every rank must "
+                               f"call with token counts on the same side of the decode (world*T <= 64) and weight-gather "
+                               f"(T >= {self.gather_min_tokens}) thresholds, and with equal T on the decode path")
+        return got
+
+    @torch.no_grad()
+    def __call__(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
+        with ops.on_device(hidden_states.device):
+            return self._call_impl(hidden_states, attention_mask, aux_balance_weight, router_logits)
+
+    def _call_impl(self, hidden_states, attention_mask, aux_balance_weight, router_logits):
+        import torch.distributed as dist
+
         B, S, H = hidden_states.shape
         T = B * S
-        if router_logits is None and self.m.stage_hook is None and self.decode_applicable(T, hidden_states.dtype):
+        path = choose_path(T, self.world, hidden_states.dtype, self.mode, self.gather_min_tokens,
+                           decode_ok=(router_logits is None and self.m.stage_hook is None and aux_balance_weight is None
+                                      and self.decode_applicable(T, hidden_states.dtype)))
+        if router_logits is not None and path == "gather":
+            path = "dispatch"
+        if self.check_lockstep:
+            self._check_lockstep(T, path)
+        self.last_path = path
+        self._call += 1
+        if path == "decode":
             out = self.decode_forward(hidden_states, attention_mask)
-            if getattr(self.m, "avg_hidden_states_last", False):
-                dist.all_reduce(out[0], op=dist.ReduceOp.SUM, group=self.group)
-                out[0].div_(self.world)
-            return out
+        elif path == "gather":
+            out = self.gather_forward(hidden_states, attention_mask, aux_balance_weight)
+        else:
+            if aux_balance_weight is not None:
+                raise NotImplementedError("aux_balance_weight on the token-dispatch expert-parallel path: use "
+                                          "DCMOE_EP_MODE=gather (the weighted loss is a per-rank quantity there too)")
+            out = self.dispatch_forward(hidden_states, attention_mask, router_logits)
+        if getattr(self.m, "avg_hidden_states_last", False):
+            # core.py:355-356: all_reduce(final_hidden_states, AVG) over the expert-parallel group in eval mode
+            dist.all_reduce(out[0], op=dist.ReduceOp.SUM, group=self.group)
+            out[0].div_(self.world)
+        return out
+
+    def dispatch_forward(self, hidden_states: torch.Tensor, attention_mask=None, router_logits=None):
+        import torch.distributed as dist
+
+        B, S, H = hidden_states.shape
+        T = B * S
         x = hidden_states.reshape(T, H)
         if not x.is_contiguous():
             x = x.contiguous()
         self.pack_local_weights()
-        ws = self.ensure_workspace(T, x.dtype, x.device, ipc=True)
-        if self._peer is None:
-            self._exchange_handles()
+        ctx = self.context(x.dtype, x.device)
+        if ctx.ws_full is None:
+            # first dispatch call of the group (collective by construction): agree on the per-rank token bound.  The
+            # workspace serves every later call with T <= max_tokens on every rank; larger calls take the weight-gather
+            # path in auto mode, so it never has to grow there.
+            got = [None] * self.world
+            dist.all_gather_object(got, T, group=self.group)
+            bound = max(got) if self.mode == "dispatch" else max(max(got), self.gather_min_tokens)
+            ctx.configure_dispatch(bound)
+        if T > ctx.max_tokens:
+            raise RuntimeError(f"expert-parallel dispatch workspace holds {ctx.max_tokens} tokens per rank, got {T}: call "
+                               f"ExpertParallelDCMoE.ctx.configure_dispatch(max_tokens) on every rank first")
+        self.ws = ctx.dispatch_workspace(T)
+        self._peer = ctx.peer
+        self.m.last_workspace = self.ws
         hook = self.m.stage_hook or (lambda _n: None)
         main = torch.cuda.current_stream()
         vec = self.phase_route(x, attention_mask, router_logits)
-        all_counts = torch.empty((self.world, vec.numel()), dtype=torch.int32, device=x.device)
-        dist.all_gather_into_tensor(all_counts, vec, group=self.group)          # also the "buffers are free" barrier
+        n = vec.numel()
+        if ctx.use_flags:
+            # all-gather of (counts, T) through peer memory; also the "buffers are free" barrier: a rank gets here only
+            # after its combine of the previous call, so when everyone has arrived nobody still reads anybody's y
+            par = ctx.epoch[SLOT_COUNTS] & 1          # two tables, alternating from one exchange to the next
+            dst = _ptr_array([p + par * MAX_RANKS * 16 * 4 for p in ctx._peer_counts_raw])
+            ctx.barrier(SLOT_COUNTS, vec, dst)
+            all_counts = ctx.counts_table.view(torch.int32, (2 * MAX_RANKS * 16,))[par * MAX_RANKS * 16:
+                                                                                    par * MAX_RANKS * 16 + self.world * n].view(self.world, n)
+        else:
+            all_counts = torch.empty((self.world, n), dtype=torch.int32, device=x.device)
+            dist.all_gather_into_tensor(all_counts, vec, group=self.group)
         hook("allgather_counts")
         self.phase_plan(all_counts)
         out = torch.empty((B, S, H), dtype=x.dtype, device=x.device)
-        tcgen05 = (self.m.ffn_impl in (None, 0, 2)) and x.dtype == torch.bfloat16
+        tcgen05 = (self.m.ffn_impl in (None, 0)) and x.dtype == torch.bfloat16
         if not (self.overlap and tcgen05):
             self.phase_dispatch()
             hook("ep_dispatch")
-            dist.all_reduce(self._flag, group=self.group)                        # every rank's rows have landed
+            ctx.barrier(SLOT_DISPATCH)                                            # every rank's rows have landed
             hook("barrier_dispatch")
             self.phase_ffn(1, 0, "ffn_gemm1")
             self.phase_ffn(2, 0, "ffn_gemm2")
-            dist.all_reduce(self._flag, group=self.group)                        # every owner's y is complete
+            ctx.barrier(SLOT_FFN)                                                 # every owner's y is complete
             hook("barrier_ffn")
             self.phase_combine(out.view(T, H), 0)
             hook("ep_combine")
@@ -442,7 +763,6 @@ class ExpertParallelDCMoE:
             if self._side is None:
                 self._side = torch.cuda.Stream(x.device)
                 self._ev = [torch.cuda.Event() for _ in range(4)]
-                self._flag2 = torch.zeros(1, dtype=torch.int32, device=x.device)
             side, ev = self._side, self._ev
             ev[0].record(main)
             timed = self.m.stage_hook is not None
@@ -455,15 +775,14 @@ class ExpertParallelDCMoE:
                 if timed:
                     t1.record(side)
                     self.comm_events.append(("ep_dispatch", t0, t1))
-                dist.all_reduce(self._flag2, group=self.group)                   # barrier 1 (on the comm stream)
+                ctx.barrier(SLOT_DISPATCH)                                        # barrier 1 (on the comm stream)
                 ev[1].record(side)
-            ss = self.shared_split if self.m.ffn_impl in (None, 0) else 0
-            self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas, ss)         # overlaps the dispatch (first ss/8 of the tiles)
+            self.phase_ffn(1, 1, "ffn_gemm1_shared", self.gemm_ctas)             # overlaps the dispatch
             main.wait_event(ev[1])
             hook("wait_dispatch")
             self.phase_ffn(1, 2, "ffn_gemm1_routed")
             self.phase_ffn(2, 2, "ffn_gemm2_routed")
-            dist.all_reduce(self._flag, group=self.group)                        # barrier 2: routed y complete everywhere
+            ctx.barrier(SLOT_FFN)                                                 # barrier 2: routed y complete everywhere
             hook("barrier_ffn")
             ev[2].record(main)
             with torch.cuda.stream(side):
@@ -476,17 +795,11 @@ class ExpertParallelDCMoE:
                     t3.record(side)
                     self.comm_events.append(("ep_combine_gather", t2, t3))
                 ev[3].record(side)
-            if ss:                                                               # rest of the shared GEMM-1 + GEMM-2 overlap
-                self.phase_ffn(1, 3, "ffn_gemm1_shared_rest", self.gemm_ctas, ss)   # the combine gather
             self.phase_ffn(2, 1, "ffn_gemm2_shared", self.gemm_ctas)
             main.wait_event(ev[3])
             hook("wait_combine")
             self.phase_combine(out.view(T, H), 2)
             hook("ep_combine_final")
-        if getattr(self.m, "avg_hidden_states_last", False):
-            # core.py:355-356: all_reduce(final_hidden_states, AVG) over the expert-parallel group in eval mode
-            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
-            out.div_(self.world)
         logits, top_k, mask, gw = self._route
         return out, logits, top_k, mask, gw, self._aux
 
@@ -502,8 +815,8 @@ class LocalRanks:
 
     @torch.no_grad()
     def decode_forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
-        """The decode-sized expert-parallel path (ExpertParallelDCMoE.decode_forward) with the all-gather replaced by
-        a torch.cat and the peers' y buffers by the virtual ranks' own.  Every x must have the same token count."""
+        """The decode-sized expert-parallel path (ExpertParallelDCMoE.decode_forward) with the push of the token rows
+        replaced by a torch.cat and the peers' y buffers by the virtual ranks' own.  Every x must have the same token count."""
         flat = [x.reshape(-1, x.shape[-1]).contiguous() for x in xs]
         T = flat[0].shape[0]
         assert all(f.shape[0] == T for f in flat)
@@ -525,14 +838,29 @@ class LocalRanks:
         return outs
 
     @torch.no_grad()
+    def gather_forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
+        """The weight-gather path: every virtual rank copies all ranks' packs (local pointers here) into its staging
+        pack and runs the single-GPU forward on its own tokens."""
+        for ep in self.ranks:
+            ep.pack_local_weights()
+            ep.context(xs[0].dtype, xs[0].device)
+        for ep in self.ranks:
+            ep.set_peer_weights([q._wbuf["w13"].ptr for q in self.ranks], [q._wbuf["w2"].ptr for q in self.ranks])
+        return [ep.gather_forward(xs[r], None if attention_masks is None else attention_masks[r])
+                for r, ep in enumerate(self.ranks)]
+
+    @torch.no_grad()
     def forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
-        R = self.world
         shapes = [x.shape for x in xs]
         flat = [x.reshape(-1, x.shape[-1]).contiguous() for x in xs]
-        T_global = sum(f.shape[0] for f in flat)
+        T_max = max(f.shape[0] for f in flat)
         for r, ep in enumerate(self.ranks):
             ep.pack_local_weights()
-            ep.ensure_workspace(flat[r].shape[0], flat[r].dtype, flat[r].device, ipc=False, T_global=T_global)
+            ctx = ep.context(flat[r].dtype, flat[r].device)
+            if ctx.ws_full is None or ctx.max_tokens < T_max:
+                ctx.configure_dispatch(T_max)
+            ep.ws = ctx.dispatch_workspace(flat[r].shape[0])
+            ep.m.last_workspace = ep.ws
         for ep in self.ranks:
             ep.set_peers([q.ws.x_packed.data_ptr() for q in self.ranks], [q.ws.row_scale.data_ptr() for q in self.ranks],
                          [q.ws.y.data_ptr() for q in self.ranks])
@@ -553,7 +881,7 @@ class LocalRanks:
                 outs.append((out.view(shapes[r]), logits, top_k, mask, gw, ep._aux))
         else:   # the kernel sequence of the overlapped schedule (run serially here)
             for ep in self.ranks:
-                ep.phase_ffn(1, 1, shared_split=ep.shared_split)   # (part of the) shared GEMM-1 needs nothing from the dispatch
+                ep.phase_ffn(1, 1)          # the shared GEMM-1 needs nothing from the dispatch
             for ep in self.ranks:
                 ep.phase_dispatch()
             for ep in self.ranks:
@@ -562,8 +890,6 @@ class LocalRanks:
             for ep in self.ranks:
                 ep.phase_combine(None, 1)
             for ep in self.ranks:
-                if ep.shared_split:
-                    ep.phase_ffn(1, 3, shared_split=ep.shared_split)
                 ep.phase_ffn(2, 1)
             outs = []
             for r, ep in enumerate(self.ranks):

@@ -52,6 +52,52 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class on_device:
+    """Make ``device`` the current CUDA device for the launches inside the block (the C side launches on the current
+    device, and the stream handed to it must belong to that device).  Costs nothing when it already is current --
+    the reference's PyTorch ops guard the device the same way, so a layer that lives on cuda:1 works from a process
+    whose current device is cuda:0."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        device = torch.device(device)
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = -1
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def guarded(fn):
+    """Run ``fn`` with the device of its workspace / first tensor argument current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, Workspace):
+                dev = a.device
+                break
+            if isinstance(a, torch.Tensor) and a.is_cuda and dev is None:
+                dev = a.device
+        if dev is None:
+            return fn(*args, **kwargs)
+        with on_device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def query_sizes(dims: LayerDims, dtype: torch.dtype, T: int, row_capacity: int = 0):
     lib = _lib.load()
     cfg = dims.c_config(dtype)
@@ -85,6 +131,12 @@ class Workspace:
         self.slot_of = torch.empty((max(T, 1), dims.n_real), dtype=torch.int32, device=dev)
         self.row_token = torch.full((self.row_capacity,), -1, dtype=torch.int32, device=dev)
         self._c_ws = None
+        # a row_capacity below the worst case can overflow (rows dropped, plan.overflow = 1): the flag is copied to pinned
+        # host memory after every forward and examined, without blocking, before the next one
+        worst = self.t_pad + dims.n_real * T + _lib.TILE_M * dims.n_real
+        self.reduced = self.row_capacity < worst
+        self._ovf_host = None
+        self._ovf_event = None
 
     def c_workspace(self) -> DcmoeWorkspace:
         """The dcmoe_workspace struct of this workspace's buffers (built once; the buffers never move)."""
@@ -116,6 +168,30 @@ class Workspace:
         default worst-case capacity can never overflow."""
         return bool(self._view(self.layout.overflow, 1, torch.int32).item())
 
+    def note_overflow_async(self):
+        """Enqueue the copy of the plan's overflow flag to pinned host memory (no synchronisation)."""
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._ovf_event = torch.cuda.Event()
+        self._ovf_host.copy_(self._view(self.layout.overflow, 1, torch.int32), non_blocking=True)
+        self._ovf_event.record(torch.cuda.current_stream(self.device))
+
+    def raise_if_overflowed(self, block: bool = False):
+        """Raise if a forward that used this workspace dropped rows because ``row_capacity`` was too small.  With
+        ``block=False`` only flags whose copy has already completed are examined."""
+        if self._ovf_event is None:
+            return
+        if block:
+            self._ovf_event.synchronize()
+        elif not self._ovf_event.query():
+            return
+        if int(self._ovf_host[0]) != 0:
+            self._ovf_host[0] = 0
+            raise _lib.DcmoeError(
+                f"DCMoE workspace overflow: the routed rows of a forward over {self.T} tokens did not fit row_capacity="
+                f"{self.row_capacity}; rows were dropped and that call's output is incomplete.  Raise row_capacity / "
+                f"row_capacity_factor (worst case: every token to every routed expert)")
+
     @property
     def aux_loss(self) -> torch.Tensor:
         return self._view(self.layout.aux_loss, 1, torch.float32)
@@ -126,6 +202,7 @@ class Workspace:
         return self._view(self.layout.mtiles, n * 4, torch.int32).view(n, 4)
 
 
+@guarded
 def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Workspace, logits_in: Optional[torch.Tensor] = None,
            attention_mask: Optional[torch.Tensor] = None):
     """Top-P router.  Returns (full_router_logits, dynamic_top_k, expert_mask, global_weight)."""
@@ -150,6 +227,7 @@ def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Worksp
     return logits, top_k, mask, gw
 
 
+@guarded
 def front_small(x: torch.Tensor, w_gate: torch.Tensor, ws: Workspace, attention_mask: Optional[torch.Tensor] = None):
     """router + plan + permute in one launch (bf16, T <= 64).  Returns what ``router`` returns."""
     lib = _lib.load()
@@ -170,11 +248,13 @@ def front_small(x: torch.Tensor, w_gate: torch.Tensor, ws: Workspace, attention_
     return logits, top_k, mask, gw
 
 
+@guarded
 def plan(ws: Workspace):
     lib = _lib.load()
     _lib.check(lib.dcmoe_plan(ws.T, ws.row_capacity, ws.cfg, _ptr(ws.plan), _stream()), "dcmoe_plan")
 
 
+@guarded
 def permute(x: torch.Tensor, expert_mask: torch.Tensor, global_weight: torch.Tensor, ws: Workspace):
     lib = _lib.load()
     _lib.check(lib.dcmoe_permute(_ptr(x), _ptr(expert_mask), _ptr(global_weight), ws.T, ws.row_capacity,
@@ -182,6 +262,7 @@ def permute(x: torch.Tensor, expert_mask: torch.Tensor, global_weight: torch.Ten
                                  _ptr(ws.row_token), _ptr(ws.row_scale), _stream()), "dcmoe_permute")
 
 
+@guarded
 def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Workspace, impl: int = 0, phase: int = 0):
     lib = _lib.load()
     _lib.check(lib.dcmoe_grouped_ffn(_ptr(x), _ptr(ws.x_packed), _ptr(w13), _ptr(w2), _ptr(ws.row_scale), ws.T,
@@ -189,6 +270,7 @@ def grouped_ffn(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Worksp
                                      impl, phase, _stream()), "dcmoe_grouped_ffn")
 
 
+@guarded
 def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] = None,
             aux_out: Optional[torch.Tensor] = None):
     """Combine (+ optional fused residual add).  With ``aux_out`` (a float32 scalar tensor) the same launch also copies
@@ -203,6 +285,7 @@ def combine(ws: Workspace, out: torch.Tensor, residual: Optional[torch.Tensor] =
                    "dcmoe_combine_aux")
 
 
+@guarded
 def forward(x: torch.Tensor, w_gate: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor, ws: Workspace, out: torch.Tensor,
             attention_mask: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, impl: int = 0):
     """The whole layer in ONE host call (``dcmoe_forward``).  Returns (logits, top_k, mask, gw, aux)."""
@@ -248,6 +331,7 @@ def stream_segments(n_mtiles: int, granules_per_tile: int, grid: int):
     return out
 
 
+@guarded
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, out: Optional[torch.Tensor] = None):
     """Qwen2RMSNorm of [T, H] rows (the decoder layer's post_attention_layernorm, model.py:240)."""
     lib = _lib.load()
@@ -262,6 +346,7 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, dims: LayerDims, 
     return out
 
 
+@guarded
 def pack_expert(gate_proj: torch.Tensor, up_proj: torch.Tensor, down_proj: torch.Tensor, group: int, part: int,
                 dims: LayerDims, w13: torch.Tensor, w2: torch.Tensor):
     lib = _lib.load()
