@@ -133,3 +133,41 @@ def test_route_edge_cases():
     lg[0, 8] = 10.0
     top_k, mask, gw, _ = R.route(lg)
     assert mask[0, 8] == 1 and mask[0, :8].sum() == 0
+
+
+# ------------------------------------------------------------------ the real reference block -> DCMoE (build container only)
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).reference_available(),
+                    reason="the reference tree (/root/reference) only exists in the build container")
+def test_real_reference_block_loads_into_dcmoe_strict():
+    """the drop-in claims of INTEGRATION.md, checked against the UNMODIFIED reference class:
+    identical state-dict keys and shapes (load_state_dict strict=True both ways), ``DCMoE.from_reference`` reads the
+    block's configuration back, and the reference model's ``_init_weights`` isinstance hook (model.py:275-278) works on
+    the replacement once the symbol is rebound."""
+    from oracle import ref_loader
+    from unimoe_audio_b200 import DCMoE, UniMoEAudioSparseMoeBlock
+
+    block = ref_loader.build_reference_block(dtype=torch.bfloat16, seed=4)
+    cfg = ref_loader.reference_text_config()
+    ours = DCMoE(cfg).to(torch.bfloat16)
+    sd = block.state_dict()
+    assert list(sd.keys()) == list(ours.state_dict().keys())
+    assert all(sd[k].shape == v.shape and sd[k].dtype == v.dtype for k, v in ours.state_dict().items())
+    res = ours.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    block.load_state_dict(ours.state_dict(), strict=True)           # and back
+    assert all(torch.equal(sd[k], v) for k, v in ours.state_dict().items())
+    # from_reference: every constructor scalar the reference stores is read back (core.py:204-234)
+    twin = DCMoE.from_reference(block)
+    for attr in ("hidden_dim", "mlp_dynamic_expert_num", "mlp_dynamic_real_expert_num", "mlp_dynamic_null_expert_num",
+                 "mlp_dynamic_top_p", "mlp_dynamic_top_k", "mlp_fixed_expert_num", "num_experts", "router_jitter_noise",
+                 "token_drop", "drop_policy", "capacity_factor", "min_capacity", "fp32_gate", "avg_hidden_states_last"):
+        assert getattr(twin, attr) == getattr(block, attr), attr
+    assert twin.dims.dynamic_intermediate_size == cfg["dynamic_intermediate_size"]
+    assert twin.dims.shared_intermediate_size == cfg["shared_intermediate_size"]
+    assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), sd.values()))
+    # the rebind of INTEGRATION.md section 1: model.py:275 does isinstance(module, UniMoEAudioSparseMoeBlock)
+    assert UniMoEAudioSparseMoeBlock is DCMoE and isinstance(twin, UniMoEAudioSparseMoeBlock)
+    twin.gate.weight.data.normal_(mean=0.0, std=0.02)                # what _init_weights does to the block (model.py:276-278)
+    # sub-module paths the reference touches (core.py:356, :510)
+    assert twin.dynamic_real_moe.deepspeed_moe.ep_group is None
+    assert len(twin.dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts) == cfg["mlp_dynamic_expert_num"]

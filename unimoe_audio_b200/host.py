@@ -32,6 +32,7 @@ class HostPipeline:
         self.step = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._last_out = None
 
     def submit(self, x_host: torch.Tensor, attention_mask=None):
         """Enqueue one step.  ``x_host`` must be pinned.  Returns nothing; call ``result()`` in order."""
@@ -63,6 +64,7 @@ class HostPipeline:
             self.ev_d2h[slot].record(self.s_out)
         self.h2d_bytes = x_host.numel() * x_host.element_size()
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in out)
+        self._last_out = out
         self.pending.append(slot)
         self.step += 1
 
@@ -72,6 +74,27 @@ class HostPipeline:
         slot = self.pending.popleft()
         self.ev_d2h[slot].synchronize()
         return tuple(self.out_host[slot])
+
+    def copy_only_ms(self, x_host: torch.Tensor, steps: int) -> float:
+        """Device time of ``steps`` rounds of one step's copies alone -- the H2D of ``x_host`` and the D2H of the last
+        step's 6-tuple, on the two copy streams at once, no kernels: the host-side ceiling of the pipeline on this box
+        (PCIe, host memory, NUMA placement), to be compared with the end-to-end step time."""
+        if getattr(self, "_last_out", None) is None or self.pending:
+            raise RuntimeError("copy_only_ms needs a drained pipeline that has run at least one step")
+        torch.cuda.synchronize(self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(self.s_in)
+        ev[2].record(self.s_out)
+        for _ in range(steps):
+            with torch.cuda.stream(self.s_in):
+                self.x_dev[0].copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(self.s_out):
+                for h, t in zip(self.out_host[0], self._last_out):
+                    h.copy_(t, non_blocking=True)
+        ev[1].record(self.s_in)
+        ev[3].record(self.s_out)
+        torch.cuda.synchronize(self.device)
+        return max(ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]))
 
     def run(self, xs_host) -> List[Tuple[torch.Tensor, ...]]:
         outs = []
