@@ -16,7 +16,10 @@
  *   - audio_sparse_expert_mixer (eval branch)   utils/UniMoE_Audio_core.py:94-119, :139-154
  *   - scatter / one-hot / normalise             utils/UniMoE_Audio_core.py:259-291
  *   - calculate_audio_global_routing_weight     utils/UniMoE_Audio_core.py:178-193
- *   - audio_load_balancing_loss_func            utils/UniMoE_Audio_core.py:361-389
+ *   - audio_load_balancing_loss_func            utils/UniMoE_Audio_core.py:361-389  (both branches: plain means and
+ *                                               the aux_balance_weight-weighted means of :380-385)
+ *   - token drop, mask + renormalise step       utils/UniMoE_Audio_core.py:316, :326-329  (given the per-token keep mask;
+ *                                               the capacity selection of :303-315 is oracle/dcmoe_oracle.py::drop_keep_mask)
  *
  * Arithmetic contract ("canonical arithmetic"): the *decisions*
  * (dynamic_top_k, expert_mask) depend on floating point only through the 9-way softmax,
@@ -135,17 +138,21 @@ static float row_sum8(const float* d, int n) {
  *   gw          [T, E] fp32 storage (D-rounded values)
  *   aux_out     [1] fp32  -- audio_load_balancing_loss_func with aux_balance_weight = None
  */
-/* fixed_k > 0: mlp_dynamic_top_p == 0 -- every token selects fixed_k (= mlp_dynamic_top_k) experts, core.py:256-257 */
-int dcmoe_oracle_route_k(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
-                         int bf16, double top_p, double eps, int fixed_k, int64_t* top_k, int32_t* mask, float* gw,
-                         float* aux_out) {
+/* fixed_k > 0: mlp_dynamic_top_p == 0 -- every token selects fixed_k (= mlp_dynamic_top_k) experts, core.py:256-257
+ * keep   [T, E] uint8 or NULL: token_drop's capacity mask (core.py:313-316); a dynamic column survives only where keep
+ *        is non-zero.  The aux loss is computed BEFORE the drop (core.py:293-300 precede :302), the routing weights are
+ *        zeroed where the final mask is zero and normalised again (core.py:328-329), the global weights use the final mask.
+ * aux_w  [T] float or NULL: aux_balance_weight (core.py:380-385), weighted means instead of plain means. */
+int dcmoe_oracle_route_ex(const float* logits, const int32_t* attn_mask, const uint8_t* keep, const float* aux_w, int64_t T,
+                          int n_dyn, int n_fix, int bf16, double top_p, double eps, int fixed_k, int64_t* top_k,
+                          int32_t* mask, float* gw, float* aux_out) {
     const int E = n_dyn + n_fix;
     if (E > MAX_E || n_dyn < 1) return -1;
     const float thr_p = rnd((float)top_p, bf16);
     const float thr_eps = rnd((float)(2.0 * eps), bf16);
     const float plus_eps = rnd(1e-6f, bf16);
     const float finfo_min = bf16 ? -3.3895313892515355e38f : -3.4028234663852886e38f;
-    double tok_sum[MAX_E], prob_sum[MAX_E];
+    double tok_sum[MAX_E], prob_sum[MAX_E], w_sum = 0.0;
     for (int j = 0; j < E; ++j) tok_sum[j] = prob_sum[j] = 0.0;
 
     for (int64_t t = 0; t < T; ++t) {
@@ -213,7 +220,24 @@ int dcmoe_oracle_route_k(const float* logits, const int32_t* attn_mask, int64_t 
             float ml[MAX_E], ga[MAX_E];
             for (int j = 0; j < n_dyn; ++j) ml[j] = mk[j] ? l[j] : finfo_min;
             softmax_D(ml, n_dyn, bf16, ga);
-            for (int j = 0; j < n_dyn; ++j) { tok_sum[j] += (double)mk[j]; prob_sum[j] += (double)ga[j]; }
+            if (aux_w) {   /* core.py:384-385: mask.float() * w (fp32) and global_weight * w (a D tensor) */
+                const float w = aux_w[t];
+                w_sum += (double)w;
+                for (int j = 0; j < n_dyn; ++j) { tok_sum[j] += (double)((float)mk[j] * w); prob_sum[j] += (double)rnd(ga[j] * w, bf16); }
+            } else {
+                for (int j = 0; j < n_dyn; ++j) { tok_sum[j] += (double)mk[j]; prob_sum[j] += (double)ga[j]; }
+            }
+        }
+        /* ---- token drop: core.py:316 (mask AND capacity mask), :328-329 (zero the dropped weights, normalise again) ---- */
+        if (keep) {
+            const uint8_t* kp = keep + t * E;
+            for (int j = 0; j < n_dyn; ++j) {
+                if (!kp[j]) mk[j] = 0;
+                if (!mk[j]) rw[j] = 0.0f;            /* masked_fill(~expert_mask.bool(), 0): also where the padding mask cleared it */
+            }
+            float rs2 = rnd(row_sum8(rw, n_dyn), bf16);
+            float den2 = rnd(rs2 + plus_eps, bf16);
+            for (int j = 0; j < n_dyn; ++j) rw[j] = rnd(rw[j] / den2, bf16);
         }
         /* ---- global weights: core.py:188-192 ---- */
         {
@@ -228,9 +252,10 @@ int dcmoe_oracle_route_k(const float* logits, const int32_t* attn_mask, int64_t 
     }
     if (aux_out) {
         double acc = 0.0;
+        const double den = aux_w ? w_sum : (double)T;
         for (int j = 0; j < n_dyn; ++j) {
-            float tpe = (float)(tok_sum[j] / (double)T);
-            float rp = rnd((float)(prob_sum[j] / (double)T), bf16);
+            float tpe = (float)(tok_sum[j] / den);
+            float rp = rnd((float)(prob_sum[j] / den), bf16);
             acc += (double)(tpe * rp);
         }
         *aux_out = (float)acc * (float)n_dyn;
@@ -243,6 +268,13 @@ float dcmoe_oracle_exp_sleef(float x) { return exp_sleef_u10(x); }
 float dcmoe_oracle_exp_cr(float x) { return exp_cr(x); }
 float dcmoe_oracle_bf16_round(float x) { return bf16_round(x); }
 void dcmoe_oracle_softmax(const float* v, int n, int bf16, float* out) { softmax_D(v, n, bf16, out); }
+
+int dcmoe_oracle_route_k(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
+                         int bf16, double top_p, double eps, int fixed_k, int64_t* top_k, int32_t* mask, float* gw,
+                         float* aux_out) {
+    return dcmoe_oracle_route_ex(logits, attn_mask, NULL, NULL, T, n_dyn, n_fix, bf16, top_p, eps, fixed_k, top_k, mask, gw,
+                                 aux_out);
+}
 
 int dcmoe_oracle_route(const float* logits, const int32_t* attn_mask, int64_t T, int n_dyn, int n_fix,
                        int bf16, double top_p, double eps, int64_t* top_k, int32_t* mask, float* gw,

@@ -27,6 +27,12 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
             ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ]
+        _LIB.dcmoe_oracle_route_ex.restype = ctypes.c_int
+        _LIB.dcmoe_oracle_route_ex.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+            ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_void_p,
+        ]
         _LIB.dcmoe_oracle_exp_sleef.restype = ctypes.c_float
         _LIB.dcmoe_oracle_exp_sleef.argtypes = [ctypes.c_float]
         _LIB.dcmoe_oracle_exp_cr.restype = ctypes.c_float
@@ -35,7 +41,8 @@ def lib():
 
 
 def route(logits: torch.Tensor, attention_mask: torch.Tensor | None = None, n_dyn: int = 9, n_fix: int = 2,
-          top_p: float = 0.7, eps: float = 0.01, fixed_top_k: int = 0):
+          top_p: float = 0.7, eps: float = 0.01, fixed_top_k: int = 0, keep: torch.Tensor | None = None,
+          aux_weight: torch.Tensor | None = None):
     """Route ``logits`` [T, n_dyn+n_fix] (fp32 or bf16, CPU).
 
     Returns (dynamic_top_k int64 [T], expert_mask int32 [T,E], global_weight D [T,E], aux_loss fp32 0-dim),
@@ -59,8 +66,16 @@ def route(logits: torch.Tensor, attention_mask: torch.Tensor | None = None, n_dy
     mask = np.empty((T, E), dtype=np.int32)
     gw = np.empty((T, E), dtype=np.float32)
     aux = np.zeros((1,), dtype=np.float32)
-    rc = lib().dcmoe_oracle_route_k(
-        lg.ctypes.data, am.ctypes.data if am is not None else None, T, n_dyn, n_fix,
+    kp = aw = None
+    if keep is not None:          # token_drop capacity mask [T, E] (core.py:313-316)
+        kp = np.ascontiguousarray(keep.detach().cpu().to(torch.uint8).numpy())
+        assert kp.shape == (T, E)
+    if aux_weight is not None:    # aux_balance_weight [T] (core.py:380-385)
+        aw = np.ascontiguousarray(aux_weight.detach().cpu().reshape(-1).to(torch.float32).numpy())
+        assert aw.shape[0] == T
+    rc = lib().dcmoe_oracle_route_ex(
+        lg.ctypes.data, am.ctypes.data if am is not None else None, kp.ctypes.data if kp is not None else None,
+        aw.ctypes.data if aw is not None else None, T, n_dyn, n_fix,
         1 if dt == torch.bfloat16 else 0, float(top_p), float(eps), fixed,
         top_k.ctypes.data, mask.ctypes.data, gw.ctypes.data, aux.ctypes.data)
     if rc != 0:

@@ -60,12 +60,14 @@ def test_local_ranks_match_single_gpu(setup, world, tokens, split):
         assert ep.ws.counts.cpu().tolist()[:n_loc] == tot
 
 
-@pytest.mark.parametrize("world,tokens", [(2, [300, 300]), (4, [257, 16, 1, 130]), (8, [64] * 8)])
+@pytest.mark.parametrize("world,tokens", [(2, [300, 300]), (4, [257, 96, 65, 130]), (8, [80] * 8)])
 def test_weight_gather_path_matches_single_gpu(setup, world, tokens):
     """Weight-gather expert parallelism on virtual ranks: every rank copies all ranks' packs into its staging pack
     (dcmoe_ep_fetch_weights) and runs the single-GPU forward on its own rows -> each rank's 6-tuple (except the aux loss,
     which is per rank) is bit-equal to the single-GPU layer on the concatenated batch.  Called twice with different
-    inputs: the second call uses the other staging slot and must not see stale weights or rows."""
+    inputs: the second call uses the other staging slot and must not see stale weights or rows.  (More than 64 tokens
+    per rank -- the path is meant for thousands: at T <= 64 the layer picks the decode-sized GEMMs, whose GEMM-2 sums
+    four accumulators, i.e. equal up to fp32 reassociation only.)"""
     from unimoe_audio_b200.ep import LocalRanks
     m, W, dev, dt = setup
     lr = LocalRanks(m, world)

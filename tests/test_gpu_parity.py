@@ -361,8 +361,8 @@ def test_decode_sized_weight_streaming_ffn_matches_large_tiles(T, masked, dev):
     out_small = [t.clone() for t in m(x, mask, None)]
     with _env("DCMOE_FFN_STREAM_KSPLIT", "0"):          # GEMM-2 with one accumulator: same summation order
         out_exact = [t.clone() for t in m(x, mask, None)]
-    m.ffn_impl = 2
-    out_large = m(x, mask, None)
+    with _env("DCMOE_FFN_STREAM", "0"):                 # the 128 x 256 tile kernel at this size
+        out_large = m(x, mask, None)
     torch.cuda.synchronize()
     m.ffn_impl = None
     assert torch.equal(out_small[3], out_large[3])
@@ -461,8 +461,8 @@ def test_weight_streaming_ffn_on_a_capped_grid(max_ctas, dev):
     dt = torch.bfloat16
     m, W = _module(dt, dev, seed=2)
     x = torch.randn(9, 1, 2048, generator=torch.Generator().manual_seed(77)).to(dt).to(dev)
-    m.ffn_impl = 2
-    m(x, None, None)
+    with _env("DCMOE_FFN_STREAM", "0"):                 # reference: the 128 x 256 tile kernel
+        m(x, None, None)
     torch.cuda.synchronize()
     ws = m.last_workspace
     h_ref, y_ref = ws.h.clone(), ws.y.clone()
@@ -721,9 +721,9 @@ def test_decode_sized_kernels_random_sweep(dev):
         with _env("DCMOE_FFN_STREAM_KSPLIT", "0"):
             a = [t.clone() for t in m(x, mask, None)]
         groups_seen.add(int(m.last_workspace.n_mtiles.item()))
-        m.ffn_impl = 2
         m.use_front_small = False
-        b = m(x, mask, None, router_logits=a[1])
+        with _env("DCMOE_FFN_STREAM", "0"):             # three-kernel front end + the 128 x 256 tile kernel
+            b = m(x, mask, None, router_logits=a[1])
         torch.cuda.synchronize()
         m.ffn_impl = None
         m.use_front_small = True

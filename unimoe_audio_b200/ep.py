@@ -424,9 +424,17 @@ class ExpertParallelDCMoE:
         if tuple(w13.shape) != (G, 2 * d.dynamic_intermediate_size, d.hidden_size) or \
                 tuple(w2.shape) != (G, d.hidden_size, d.dynamic_intermediate_size) or not (w13.is_cuda and w2.is_cuda):
             raise ValueError("packed local weights have the wrong shape for this rank's expert count")
-        self._alloc_local_packs(w13.dtype, w13.device)
-        self._w13.copy_(w13)
-        self._w2.copy_(w2)
+        if self.group is None:       # virtual ranks (one process): the tensors are used as they are
+            self._w13, self._w2 = w13.contiguous(), w2.contiguous()
+            self._wbuf = {}
+            for name, t in (("w13", self._w13), ("w2", self._w2)):
+                b = IpcBuffer.__new__(IpcBuffer)
+                b.nbytes, b.device, b.ipc, b._torch, b.ptr = t.numel() * t.element_size(), t.device, False, t, t.data_ptr()
+                self._wbuf[name] = b
+        else:                        # separate processes: the packs must live in cudaIpc-exportable memory
+            self._alloc_local_packs(w13.dtype, w13.device)
+            self._w13.copy_(w13)
+            self._w2.copy_(w2)
         self._peer_w = None
 
     def set_peer_weights(self, w13: List[int], w2: List[int]):
