@@ -104,19 +104,68 @@ def canonical_permutation(expert_mask: torch.Tensor, n_real: int):
     return [torch.nonzero(expert_mask[:, e], as_tuple=True)[0] for e in range(n_real)]
 
 
-def route(logits, attention_mask=None, cfg: dict | None = None):
+def expert_capacity(num_tokens: int, n_dyn: int, capacity_factor: float, min_capacity: int) -> int:
+    """core.py:170-175 (`_audio_expert_capacity`) + the clamp of core.py:306-308: the quotient is a Python float, the
+    product and the ceil run on a 0-dim float32 tensor."""
+    import numpy as np
+
+    cap = int(np.ceil(np.float32(num_tokens / n_dyn) * np.float32(capacity_factor)))
+    if cap < int(min_capacity):
+        cap = int(min_capacity)
+    return min(cap, int(num_tokens))
+
+
+def drop_keep_mask(logits: torch.Tensor, expert_mask: torch.Tensor, n_dyn: int, capacity: int) -> torch.Tensor:
+    """Capacity mask of drop_policy == "probs" (core.py:309-313): per dynamic column, the `capacity` tokens with the
+    largest logit among the tokens that selected the expert (unselected tokens enter torch.topk with finfo.min and are
+    cleared again by the AND of :314).  torch.topk(sorted=False) leaves the choice among TIED boundary logits to the
+    implementation; the pinned rule here (and in the CUDA kernel) is: ties go to the lower token index.  Returns
+    uint8 [T, E] (shared columns 1)."""
+    T, E = logits.shape
+    keep = torch.ones((T, E), dtype=torch.uint8)
+    lf = logits.float()
+    for e in range(n_dyn):
+        sel = expert_mask[:, e] != 0
+        col = torch.zeros(T, dtype=torch.uint8)
+        idx = torch.nonzero(sel, as_tuple=True)[0]
+        if idx.numel() <= capacity:
+            col[idx] = 1
+        else:
+            order = torch.sort(lf[idx, e], descending=True, stable=True).indices     # stable: lower token first on ties
+            col[idx[order[:capacity]]] = 1
+        keep[:, e] = col
+    return keep
+
+
+def route(logits, attention_mask=None, cfg: dict | None = None, aux_balance_weight=None):
     c = dict(DEFAULT_CONFIG)
     c.update(cfg or {})
     n_dyn = c["mlp_dynamic_expert_num"] + c["mlp_dynamic_null_expert_num"]
-    return route_oracle_c.route(logits, attention_mask, n_dyn=n_dyn, n_fix=c["mlp_fixed_expert_num"],
-                                top_p=c["mlp_dynamic_top_p"], eps=c["router_jitter_noise"],
-                                fixed_top_k=int(c.get("mlp_dynamic_top_k", 0) or 0))
+    kw = dict(n_dyn=n_dyn, n_fix=c["mlp_fixed_expert_num"], top_p=c["mlp_dynamic_top_p"], eps=c["router_jitter_noise"],
+              fixed_top_k=int(c.get("mlp_dynamic_top_k", 0) or 0),
+              aux_weight=None if aux_balance_weight is None else aux_balance_weight.reshape(-1))
+    out = route_oracle_c.route(logits, attention_mask, **kw)
+    if not c.get("token_drop", False):
+        return out
+    policy = c.get("drop_policy", "probs")
+    if policy != "probs":
+        # "position" (core.py:321-323) multiplies the shared experts' all-ones columns by the capacity test too: every
+        # token with index >= capacity loses all columns and the reference returns NaN weights for it
+        # (tests/golden/drop_position_nan.npz) -- nothing to restate
+        raise ValueError(f"drop_policy {policy!r}: only 'probs' is restated")
+    cap = expert_capacity(logits.shape[0], n_dyn, c.get("capacity_factor", 1.0), c.get("min_capacity", 8))
+    keep = drop_keep_mask(logits, out[1], n_dyn, cap)                    # from the PRE-drop mask (core.py:309)
+    top_k, mask, gw, _aux = route_oracle_c.route(logits, attention_mask, keep=keep, **kw)
+    return top_k, mask, gw, out[3]                                      # the aux loss is computed before the drop (:293)
 
 
 @torch.no_grad()
 def forward(hidden_states: torch.Tensor, weights: Dict[str, torch.Tensor], attention_mask: Optional[torch.Tensor] = None,
-            cfg: dict | None = None, logits: Optional[torch.Tensor] = None, skip_ffn: bool = False) -> OracleOutput:
-    """Eval-mode forward of ``UniMoEAudioSparseMoeBlock`` (core.py:236-358), token_drop=False.
+            cfg: dict | None = None, logits: Optional[torch.Tensor] = None, skip_ffn: bool = False,
+            aux_balance_weight: Optional[torch.Tensor] = None, fp32_gate: bool = False) -> OracleOutput:
+    """Forward of ``UniMoEAudioSparseMoeBlock`` (core.py:236-358): eval mode, or -- ``fp32_gate=True`` -- the
+    training-mode forward with the fp32 gate of core.py:240-249 (input_jitter_noise = 0, ignore_differentiable_router:
+    no random branch runs).  ``cfg["token_drop"]`` selects the capacity branch (core.py:302-329, "probs" policy).
 
     ``logits`` may be supplied to pin the router input ("bit-exact given identical router logits").
     """
@@ -130,9 +179,13 @@ def forward(hidden_states: torch.Tensor, weights: Dict[str, torch.Tensor], atten
     x = hidden_states.reshape(-1, H)
     T = x.shape[0]
     if logits is None:
-        logits = F.linear(x, weights[GATE].to(D))                       # core.py:251
+        if fp32_gate:
+            logits = F.linear(x.float(), weights[GATE].float())         # core.py:241, :249
+        else:
+            logits = F.linear(x, weights[GATE].to(D))                   # core.py:251
     am = None if attention_mask is None else attention_mask.reshape(-1)
-    top_k, mask, gw, aux = route(logits, am, c)                         # core.py:255-332
+    top_k, mask, gw, aux = route(logits, am, c, aux_balance_weight)     # core.py:255-332
+    gw = gw.to(D)                                                       # core.py:339
     perm = canonical_permutation(mask, n_real)
     counts = mask[:, :n_real].sum(0)
     final = torch.zeros((T, H), dtype=D)

@@ -64,17 +64,39 @@ def main():
         torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(e) / a.steps], device=dev, dtype=torch.float64)
         sent = out[3][:, :8].sum(0).to(torch.float64)            # rows this rank routes to each expert
+        parity = None
         if world > 1:
             allms = [torch.zeros_like(ms) for _ in range(world)]
             dist.all_gather(allms, ms)
             dist.all_reduce(sent)
+            # parity gate: the ranks' outputs, gathered, against ONE single-GPU forward of the concatenated batch
+            x_all = torch.empty((world * B, a.seq, 2048), dtype=dt, device=dev)
+            dist.all_gather_into_tensor(x_all, x)
+            lg_all = torch.empty((world * T, 11), dtype=dt, device=dev)
+            dist.all_gather_into_tensor(lg_all, logits)
+            got = []
+            for i in (0, 2, 3, 4):
+                t = out[i].contiguous()
+                g = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                dist.all_gather_into_tensor(g, t)
+                got.append(g)
+            if rank == 0:
+                ref = m(x_all, None, None, router_logits=lg_all)
+                torch.cuda.synchronize()
+                parity = all(bool(torch.equal(g.reshape(ref[i].shape), ref[i])) for g, i in zip(got, (0, 2, 3, 4)))
+                del ref
+            del x_all, lg_all, got
+            torch.cuda.empty_cache()
         else:
             allms = [ms]
         if rank == 0:
             tms = [t.item() for t in allms]
             load = sent.cpu()
             print(json.dumps({"top_p": p, "n_gpus": world, "tokens_global": T * world, "ms_per_step_max": max(tms),
-                              "ms_per_step_min": min(tms), "tokens_per_s": T * world / (max(tms) * 1e-3),
+                              "ms_per_step_min": min(tms), "rank_ms_per_step": tms,
+                              "rank_time_spread": (max(tms) - min(tms)) / max(tms),
+                              "ep_path": getattr(layer, "last_path", None), "ep_equals_single_gpu": parity,
+                              "tokens_per_s": T * world / (max(tms) * 1e-3),
                               "mean_routed_experts": load.sum().item() / (T * world),
                               "expert_load_max_over_mean": (load.max() / load.mean()).item(),
                               "rows_per_expert": [int(v) for v in load.tolist()]}), flush=True)

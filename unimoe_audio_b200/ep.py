@@ -645,7 +645,7 @@ class ExpertParallelDCMoE:
                 self.comm_events.append(("weight_fetch", t0, t1))
             ctx.slot_ready[slot].record(cs)
 
-    def gather_forward(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None):
+    def gather_forward(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
         """Weight-gather expert parallelism: pull every remote expert's packed weights over NVLink (copy engines) into a
         staging pack, then run the single-GPU forward on this rank's tokens -- router, plan and permute run while the
         copies are in flight; the staging packs are double buffered, so with the host running ahead the fetch of call
@@ -661,7 +661,7 @@ class ExpertParallelDCMoE:
         main = torch.cuda.current_stream(ctx.device)
         self.fetch_weights(slot)
         w13_full, w2_full = ctx.stage[slot]
-        out = self.m._forward_local(hidden_states, attention_mask, aux_balance_weight, None, None, w13_full, w2_full,
+        out = self.m._forward_local(hidden_states, attention_mask, aux_balance_weight, router_logits, None, w13_full, w2_full,
                                     before_ffn=lambda: main.wait_event(ctx.slot_ready[slot]))
         ctx.slot_free[slot].record(main)
         return out
@@ -691,8 +691,6 @@ class ExpertParallelDCMoE:
         path = choose_path(T, self.world, hidden_states.dtype, self.mode, self.gather_min_tokens,
                            decode_ok=(router_logits is None and self.m.stage_hook is None and aux_balance_weight is None
                                       and self.decode_applicable(T, hidden_states.dtype)))
-        if router_logits is not None and path == "gather":
-            path = "dispatch"
         if self.check_lockstep:
             self._check_lockstep(T, path)
         self.last_path = path
@@ -700,7 +698,7 @@ class ExpertParallelDCMoE:
         if path == "decode":
             out = self.decode_forward(hidden_states, attention_mask)
         elif path == "gather":
-            out = self.gather_forward(hidden_states, attention_mask, aux_balance_weight)
+            out = self.gather_forward(hidden_states, attention_mask, aux_balance_weight, router_logits)
         else:
             if aux_balance_weight is not None:
                 raise NotImplementedError("aux_balance_weight on the token-dispatch expert-parallel path: use "
