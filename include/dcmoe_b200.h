@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DCMOE_ABI_VERSION 2
+#define DCMOE_ABI_VERSION 3
 
 typedef enum dcmoe_dtype { DCMOE_F32 = 0, DCMOE_BF16 = 1 } dcmoe_dtype;
 
@@ -123,6 +123,49 @@ int dcmoe_query_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
 int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
                  const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
                  void* global_weight, void* plan, void* stream);
+
+/*
+ * Router with the branches the V2 training recipe turns on (UniMoEV2-Preview/script/training.sh:46-59).
+ *   keep         [T, E] uint8 or NULL: token_drop's capacity mask from dcmoe_drop_select.  When given, a dynamic column
+ *                survives only where keep != 0 (core.py:314-316), the dropped weights are zeroed and the weights are
+ *                normalised a second time (core.py:328-329) before the global weights (core.py:331-332).  The per-block
+ *                aux partials written to the plan are still those of the mask before the drop.
+ *   flags        DCMOE_ROUTER_FP32_GATE: the training-mode fp32 gate (core.py:240-249) on a bf16 layer: x / w_gate are
+ *                bf16 and widened on load, logits_in / logits_out are FLOAT32 and all routing arithmetic is fp32;
+ *                global_weight is still written in D (core.py:339).  Ignored on an fp32 layer.
+ */
+#define DCMOE_ROUTER_FP32_GATE 1
+int dcmoe_router_ex(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, const uint8_t* keep,
+                    int flags, int64_t T, const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
+                    void* global_weight, void* plan, void* stream);
+
+/*
+ * Token drop, drop_policy == "probs".  Replaces core.py:304 -> :170-175 (capacity) and :305-314 (per-expert
+ * torch.topk over tokens on the masked logits + scatter).  Host only: capacity = max(ceil(f32(T / n_dyn) *
+ * f32(capacity_factor)), min_capacity), clamped to T.
+ */
+int dcmoe_expert_capacity(int64_t T, const dcmoe_config* cfg, double capacity_factor, int64_t min_capacity, int64_t* capacity);
+/*   logits       [T, E] of logits_dtype (DCMOE_F32 with the fp32 gate, else D)
+ *   expert_mask  [T, E] int32: the mask BEFORE the drop (dcmoe_router's output)
+ *   key_scratch  n_dyn * T * 8 bytes
+ *   keep         [T, E] uint8 out: per dynamic column the `capacity` selected tokens with the largest logit (all of them
+ *                when at most `capacity` selected it); ties at the boundary go to the LOWER token index (torch.topk
+ *                leaves them to the implementation).  Shared columns 1.  Exact integer work (radix select). */
+int dcmoe_drop_select(const void* logits, int logits_dtype, const int32_t* expert_mask, int64_t T, const dcmoe_config* cfg,
+                      int64_t capacity, void* key_scratch, uint8_t* keep, void* stream);
+
+/*
+ * aux_balance_weight branch of the load-balancing loss.  Replaces core.py:380-385 (+ :370-374, :387-389): weighted means
+ * over tokens of the pre-drop mask and of softmax_9(logits masked with finfo.min).
+ *   weight          [T] float (the caller converts the reference's [B, S] int64 / float tensor), or NULL: the plain means of
+ *                   core.py:378-379 in the arithmetic of logits_dtype -- used with the fp32 gate on a bf16 layer, where
+ *                   dcmoe_plan would round the mean probability to bf16
+ *   integer_weights 1 when the reference tensor has an integer dtype: `global_weight * w` then stays in D (rounded to
+ *                   bf16 on a bf16 layer); 0: promoted to fp32
+ *   scratch         ceil(T / 16) * 32 floats;   aux_out [1] float
+ */
+int dcmoe_aux_weighted(const void* logits, int logits_dtype, const int32_t* expert_mask, const float* weight, int integer_weights,
+                       int64_t T, const dcmoe_config* cfg, float* scratch, float* aux_out, void* stream);
 
 /*
  * Plan: exact integer histogram -> exclusive prefix sums -> segment bases, tile table, aux loss.

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dcmoe_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
-    assert lib.dcmoe_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.dcmoe_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_query_sizes_reference_config():
@@ -69,8 +69,11 @@ def test_module_mirrors_reference_interface():
     assert len(keys) == 1 + 2 * 3 + 8 * 3
     assert m.num_experts == 11 and m.mlp_dynamic_expert_num == 9
     assert m.dynamic_real_moe.deepspeed_moe.ep_group is None
-    with pytest.raises(NotImplementedError):
-        DCMoE(dict(cfg, token_drop=True))
+    with torch.device("meta"):
+        md = DCMoE(dict(cfg, token_drop=True))                         # drop_policy defaults to "probs" (core.py:230)
+    assert md.token_drop and md.drop_policy == "probs"
+    with pytest.raises(NotImplementedError, match="NaN"):             # the reference's "position" policy is broken
+        DCMoE(dict(cfg, token_drop=True, drop_policy="position"))
     with pytest.raises(ValueError):
         DCMoE(dict(cfg, mlp_dynamic_top_p=0))                      # fixed top-k routing needs mlp_dynamic_top_k >= 1
     mk = DCMoE(dict(cfg, mlp_dynamic_top_p=0, mlp_dynamic_top_k=2))   # core.py:256-257
@@ -129,3 +132,15 @@ def test_weight_streaming_partition_covers_every_granule_once(gpg, grid):
             assert max(sizes[m]) - min(sizes[m]) <= 1
         bound = -(-gpg // (grid // 9)) if grid >= 9 else gpg            # launcher: ceil(gpg / floor(grid / G)), G = 9
         assert max(max(v) for v in sizes.values()) <= max(bound, 1)
+
+
+def test_expert_capacity_matches_the_reference_formula():
+    """core.py:170-175 + :306-308, against the reference's own tensor arithmetic restated with torch on the CPU."""
+    dims = LayerDims()
+    for T, cf, mn in [(1024, 1.0, 8), (1024, 2.0, 8), (16384, 3.0, 8), (16384, 6.0, 8), (7, 1.0, 8), (40, 1.0, 8),
+                      (262144, 1.25, 4), (999, 0.37, 8), (9, 1.0, 0)]:
+        cap = torch.ceil((T / 9) * torch.tensor(cf)).to(torch.int64)
+        if cap < torch.tensor(mn):
+            cap = torch.tensor(mn).to(torch.int64)
+        want = min(int(cap), T)
+        assert ops.expert_capacity(dims, T, cf, mn) == want, (T, cf, mn)

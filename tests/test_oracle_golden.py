@@ -171,3 +171,93 @@ def test_real_reference_block_loads_into_dcmoe_strict():
     # sub-module paths the reference touches (core.py:356, :510)
     assert twin.dynamic_real_moe.deepspeed_moe.ep_group is None
     assert len(twin.dynamic_real_moe.deepspeed_moe.experts.deepspeed_experts) == cfg["mlp_dynamic_expert_num"]
+
+
+# ------------------------------------------------------------------ token drop / aux_balance_weight / fp32 gate
+# (fixtures of tools/make_golden_drop.py: the branches the V2 training recipe turns on, UniMoEV2-Preview/script/training.sh:46-59)
+DROP_CASES = [(cf, tag) for cf in (1, 2) for tag in ("", "_masked")]
+
+
+@pytest.mark.parametrize("dname", ["fp32", "bf16"])
+@pytest.mark.parametrize("cf,tag", DROP_CASES)
+def test_token_drop_oracle_matches_reference_golden(dname, cf, tag, golden_dir):
+    """drop_policy "probs" (core.py:302-329).  fp32: the boundary logits are untied, so the kept set is unique and the
+    whole result must be bit-equal.  bf16: boundaries are tied (torch.topk's pick among equals is implementation
+    defined), so the selection is checked as a property -- per expert the kept COUNT and the multiset of kept logit
+    VALUES equal the reference's -- and the mask + renormalise step is pinned bit-exactly on the reference's own kept set."""
+    g = np.load(os.path.join(golden_dir, f"drop_{dname}.npz"))
+    dt = DT[dname]
+    logits = torch.from_numpy(g["logits"]).to(dt)
+    am = torch.from_numpy(g["attention_mask"]) if tag else None
+    key = f"cf{cf}{tag}"
+    cfg = dict(token_drop=True, drop_policy="probs", capacity_factor=float(cf), min_capacity=8)
+    top_k, mask, gw, aux = O.route(logits, None if am is None else am.reshape(-1), cfg)
+    ref_mask = torch.from_numpy(g[f"{key}_expert_mask"])
+    pre = torch.from_numpy(g["pre_mask_masked" if tag else "pre_mask"])
+    cap = O.expert_capacity(logits.shape[0], 9, float(cf), 8)
+    assert cap == {1: 114, 2: 228}[cf]
+    assert np.array_equal(top_k.numpy(), g[f"{key}_dynamic_top_k"])
+    np.testing.assert_allclose(aux.item(), float(g[f"{key}_aux_loss"]), rtol=1e-5)      # computed BEFORE the drop
+    for e in range(9):
+        assert int(mask[:, e].sum()) == int(ref_mask[:, e].sum()) == min(cap, int(pre[:, e].sum()))
+        a = np.sort(logits[mask[:, e] != 0, e].float().numpy())
+        b = np.sort(logits[ref_mask[:, e] != 0, e].float().numpy())
+        assert np.array_equal(a, b)
+    assert (mask[:, 9:] == 1).all()
+    if bool(g[f"{key}_untied"]):
+        assert dname == "fp32"
+        assert np.array_equal(mask.numpy(), ref_mask.numpy())
+        assert np.array_equal(gw.float().numpy(), g[f"{key}_global_weight"])
+    # the renormalise step on the reference's kept set (exact in both dtypes)
+    keep = ref_mask.to(torch.uint8).clone()
+    keep[:, 9:] = 1
+    if am is not None:          # a padded token's columns are cleared by the padding mask, not by the capacity
+        keep[~am.reshape(-1), :9] = 1
+    _tk, m2, gw2, _ = R.route(logits, None if am is None else am.reshape(-1), keep=keep)
+    assert np.array_equal(m2.numpy(), ref_mask.numpy())
+    assert np.array_equal(gw2.float().numpy(), g[f"{key}_global_weight"])
+
+
+def test_token_drop_position_policy_is_nan_in_the_reference(golden_dir):
+    """Why drop_policy="position" (core.py:321-323) is rejected: the reference clears the shared experts' columns too,
+    so most tokens past the capacity end with NaN weights.  Nothing to be compatible with."""
+    g = np.load(os.path.join(golden_dir, "drop_position_nan.npz"))
+    nan = g["global_weight_is_nan"]
+    assert nan.sum() > 0.5 * nan.shape[0] and not nan[: int(g["capacity"])].any()
+    assert (g["expert_mask"][int(g["capacity"]):, 9:] == 0).all()       # shared experts dropped for every later token
+    with pytest.raises(ValueError):
+        O.route(torch.from_numpy(g["logits"]), None, dict(token_drop=True, drop_policy="position"))
+
+
+@pytest.mark.parametrize("dname", ["fp32", "bf16"])
+def test_aux_balance_weight_oracle_matches_reference_golden(dname, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"auxw_{dname}.npz"))
+    dt = DT[dname]
+    logits = torch.from_numpy(g["logits"]).to(dt)
+    am = torch.from_numpy(g["attention_mask"]).reshape(-1)
+    tol = 1e-5 if dname == "fp32" else 2e-3
+    _, mask, gw, aux = O.route(logits, am, None, torch.from_numpy(g["w_int64"]))
+    np.testing.assert_allclose(aux.item(), float(g["int_aux_loss"]), rtol=tol)
+    assert np.array_equal(mask.numpy(), g["int_expert_mask"]) and np.array_equal(gw.float().numpy(), g["int_global_weight"])
+    _, mask, gw, aux = O.route(logits, None, None, torch.from_numpy(g["w_fp32"]))
+    np.testing.assert_allclose(aux.item(), float(g["float_aux_loss"]), rtol=tol)
+    assert np.array_equal(mask.numpy(), g["float_expert_mask"])
+
+
+def test_fp32_gate_training_forward_oracle_matches_reference_golden(golden_dir):
+    """Training-mode forward with fp32_gate (core.py:240-249): fp32 logits and routing arithmetic on a bf16 layer."""
+    g = np.load(os.path.join(golden_dir, "fp32gate_bf16.npz"))
+    W = O.make_weights(seed=int(g["weight_seed"]), dtype=torch.bfloat16)
+    x = torch.randn(1, 256, 2048, generator=torch.Generator().manual_seed(int(g["x_seed"]))).to(torch.bfloat16)
+    out = O.forward(x, W, fp32_gate=True)
+    assert out.full_router_logits.dtype == torch.float32 and out.global_weight.dtype == torch.bfloat16
+    np.testing.assert_allclose(out.full_router_logits.numpy(), g["full_router_logits"], rtol=0, atol=2e-6)
+    # routing pinned on the reference's own fp32 logits
+    out = O.forward(x, W, fp32_gate=True, logits=torch.from_numpy(g["full_router_logits"]))
+    assert np.array_equal(out.dynamic_top_k.numpy(), g["dynamic_top_k"])
+    assert np.array_equal(out.expert_mask.numpy(), g["expert_mask"])
+    assert np.array_equal(out.global_weight.float().numpy(), g["global_weight"])
+    np.testing.assert_allclose(out.aux_loss.item(), float(g["aux_loss"]), rtol=1e-5)
+    final = out.final_hidden_states.float().reshape(256, 2048)
+    scale = float(np.abs(g["final_rows"]).max())
+    np.testing.assert_allclose(final[::2].numpy(), g["final_rows"], rtol=1e-2, atol=1e-2 * scale)

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcmoe_b200.so")
 
 DCMOE_F32, DCMOE_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+ROUTER_FP32_GATE = 1
 ROUTER_BLOCK, TILE_M = 16, 128
 
 
@@ -53,6 +54,12 @@ SIGNATURES = {
     "dcmoe_query_sizes": (c_int, [POINTER(DcmoeConfig), c_int64, c_int64, POINTER(DcmoeSizes), POINTER(DcmoePlanLayout)]),
     "dcmoe_router": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dcmoe_router_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, POINTER(DcmoeConfig), c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dcmoe_expert_capacity": (c_int, [c_int64, POINTER(DcmoeConfig), c_double, c_int64, POINTER(c_int64)]),
+    "dcmoe_drop_select": (c_int, [c_void_p, c_int, c_void_p, c_int64, POINTER(DcmoeConfig), c_int64, c_void_p, c_void_p, c_void_p]),
+    "dcmoe_aux_weighted": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
+                                   c_void_p]),
     "dcmoe_front_small": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dcmoe_plan": (c_int, [c_int64, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p]),

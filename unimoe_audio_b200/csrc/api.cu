@@ -137,8 +137,11 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
 }
 
 // launchers implemented in the other translation units
-int launch_router(const void*, const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, void*, int64_t*,
-                  int32_t*, void*, int32_t*, float*, cudaStream_t);
+int launch_router(const void*, const void*, const void*, const int32_t*, const uint8_t*, int, int64_t, const dcmoe_config*,
+                  void*, int64_t*, int32_t*, void*, int32_t*, float*, cudaStream_t);
+int launch_drop_select(const void*, bool, const int32_t*, int64_t, const dcmoe_config*, int64_t, void*, uint8_t*, cudaStream_t);
+int launch_aux_weighted(const void*, bool, const int32_t*, const float*, bool, int64_t, const dcmoe_config*, float*, float*,
+                        cudaStream_t);
 int launch_plan(int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView, cudaStream_t);
 int launch_front_small(const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
                        void*, int64_t*, int32_t*, void*, void*, int32_t*, int32_t*, float*, cudaStream_t);
@@ -224,20 +227,58 @@ int dcmoe_query_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     if ((T_) < 0) { set_error("negative token count"); return DCMOE_ERR_INVALID; } \
     if ((rc = require_device())) return rc;
 
-int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
-                 const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight,
-                 void* plan, void* stream) {
+int dcmoe_router_ex(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, const uint8_t* keep,
+                    int flags, int64_t T, const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
+                    void* global_weight, void* plan, void* stream) {
     DCMOE_PROLOGUE(T)
     if (T > 0 && ((logits_in == nullptr && (x == nullptr || w_gate == nullptr)) || !logits_out || !top_k || !expert_mask ||
                   !global_weight || !plan)) {
         set_error("dcmoe_router: NULL pointer argument");
         return DCMOE_ERR_INVALID;
     }
+    if (flags & ~DCMOE_ROUTER_FP32_GATE) { set_error("dcmoe_router_ex: unknown flag bits 0x%x", flags); return DCMOE_ERR_INVALID; }
     dcmoe_sizes sz; dcmoe_plan_layout l;
     if ((rc = fill_sizes(cfg, T, 0, &sz, &l))) return rc;
     PlanView pv = plan_view(plan, l);
-    return launch_router(x, w_gate, logits_in, attn_mask, T, cfg, logits_out, top_k, expert_mask, global_weight,
+    return launch_router(x, w_gate, logits_in, attn_mask, keep, flags, T, cfg, logits_out, top_k, expert_mask, global_weight,
                          pv.block_counts, pv.block_probs, (cudaStream_t)stream);
+}
+
+int dcmoe_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
+                 const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask, void* global_weight,
+                 void* plan, void* stream) {
+    return dcmoe_router_ex(x, w_gate, logits_in, attn_mask, nullptr, 0, T, cfg, logits_out, top_k, expert_mask, global_weight,
+                           plan, stream);
+}
+
+int dcmoe_expert_capacity(int64_t T, const dcmoe_config* cfg, double capacity_factor, int64_t min_capacity, int64_t* capacity) {
+    int rc;
+    if ((rc = validate_config(cfg))) return rc;
+    if (!capacity || T < 0) { set_error("dcmoe_expert_capacity: bad argument"); return DCMOE_ERR_INVALID; }
+    // core.py:172: the quotient is a Python float (double); product and ceil run on a 0-dim float32 tensor
+    const float q = (float)((double)T / (double)(cfg->n_real + cfg->n_null));
+    int64_t cap = (int64_t)ceilf(q * (float)capacity_factor);
+    if (cap < min_capacity) cap = min_capacity;          // core.py:173-174
+    if (cap > T) cap = T;                                // core.py:306-308
+    *capacity = cap;
+    return DCMOE_OK;
+}
+
+int dcmoe_drop_select(const void* logits, int logits_dtype, const int32_t* expert_mask, int64_t T, const dcmoe_config* cfg,
+                      int64_t capacity, void* key_scratch, uint8_t* keep, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (T > 0 && (!logits || !expert_mask || !key_scratch || !keep)) { set_error("dcmoe_drop_select: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    if (capacity < 0 || (logits_dtype != DCMOE_F32 && logits_dtype != DCMOE_BF16)) { set_error("dcmoe_drop_select: bad capacity / dtype"); return DCMOE_ERR_INVALID; }
+    return launch_drop_select(logits, logits_dtype == DCMOE_BF16, expert_mask, T, cfg, capacity, key_scratch, keep, (cudaStream_t)stream);
+}
+
+int dcmoe_aux_weighted(const void* logits, int logits_dtype, const int32_t* expert_mask, const float* weight, int integer_weights,
+                       int64_t T, const dcmoe_config* cfg, float* scratch, float* aux_out, void* stream) {
+    DCMOE_PROLOGUE(T)
+    if (!aux_out || (T > 0 && (!logits || !expert_mask || !scratch))) { set_error("dcmoe_aux_weighted: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    if (logits_dtype != DCMOE_F32 && logits_dtype != DCMOE_BF16) { set_error("dcmoe_aux_weighted: bad dtype"); return DCMOE_ERR_INVALID; }
+    return launch_aux_weighted(logits, logits_dtype == DCMOE_BF16, expert_mask, weight, integer_weights != 0, T, cfg, scratch, aux_out,
+                               (cudaStream_t)stream);
 }
 
 // NOTE: the plan layout depends on (T, row_capacity); callers pass the same row_capacity to every call of a forward.

@@ -160,9 +160,14 @@ __device__ __forceinline__ int inverse_perm_lanes(int rank, int j, const int n) 
 // softmax inside iteration `it` has max == the it-th largest logit, e = 1 for it and exactly 0 for every
 // dropped / already selected entry, i.e. it is exactly 1 unless another remaining logit lies within 2 % of
 // the current maximum ("near tie").  Only near ties (about 3 % of iterations) evaluate it.
-template <bool BF16, int NDYN, int NE>
+//
+// DROP: the token-drop branch (core.py:314-316, :328-329) is compiled in; when `do_drop` (warp-uniform) is set, a dynamic
+// column survives only where keep_j != 0, the dropped weights are zeroed and the weights are normalised a second time.
+// The aux softmax (ga_out) is always that of the mask BEFORE the drop (core.py:293 precedes :302).
+template <bool BF16, int NDYN, int NE, bool DROP = false>
 __device__ __forceinline__ void route_token(float l, int j, int half, int am, const RouteConsts& rc, int& raw_out,
-                                            int& mask_out, float& gw_out, float& ga_out) {
+                                            int& mask_out, float& gw_out, float& ga_out, int keep_j = 1,
+                                            bool do_drop = false) {
     const int n_dyn = NDYN ? NDYN : rc.n_dyn, E = NE ? NE : rc.E;
     const float ninf = __int_as_float(0xff800000);
     const bool dyn = j < n_dyn;
@@ -231,8 +236,8 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
     const float den = rnd<BF16>(__fadd_rn(rnd<BF16>(rsum), rc.plus_eps));
     rw = rnd<BF16>(__fdiv_rn(rw, den));
     // ---- padding mask, shared experts always on (core.py:286-291) ----
-    const int mk = dyn ? sel * am : (j < E ? 1 : 0);
-    const bool any_sel = (k > 0) && (am != 0);
+    int mk = dyn ? sel * am : (j < E ? 1 : 0);
+    bool any_sel = (k > 0) && (am != 0);
     // ---- aux-loss softmax (core.py:370-373): selected logits, finfo.min elsewhere ----
     {
         // max = top1 if anything is selected (exp(finfo.min - top1) is exactly 0), else every entry is
@@ -241,6 +246,16 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
         const float ia = __fdiv_rn(1.0f, seq_sum_lanes(ea, n_dyn));
         ga_out = rnd<BF16>(__fmul_rn(ea, ia));
     }
+    if (DROP && do_drop) {
+        // ---- token drop (core.py:314-316, :326-329): AND with the capacity mask, zero the dropped weights,
+        // normalise again (torch.sum -> ATen row_sum; the same rounding points as the first normalisation) ----
+        if (dyn && !keep_j) mk = 0;
+        if (dyn && !mk) rw = 0.0f;                                    // also where the padding mask cleared the column
+        const float rs2 = row_sum8_lanes(dyn ? rw : 0.0f, n_dyn);
+        const float den2 = rnd<BF16>(__fadd_rn(rnd<BF16>(rs2), rc.plus_eps));
+        rw = rnd<BF16>(__fdiv_rn(rw, den2));
+        any_sel = (__ballot_sync(kFull, dyn && mk) & half_mask) != 0u;
+    }
     // ---- global weights (core.py:188-192): 11-way softmax over selected + shared ----
     {
         float ms = ninf;                                              // max of the shared logits
@@ -248,10 +263,17 @@ __device__ __forceinline__ void route_token(float l, int j, int half, int am, co
         for (int i = 0; i < kMaxDyn; ++i) {
             if (i >= n_dyn && i < E) ms = fmaxf(ms, __shfl_sync(kFull, l, i, 16));
         }
-        const bool reuse = any_sel && top1 >= ms;                     // softmax max == top1: same exp arguments
+        // softmax max == top1: same exp arguments (after a token drop the largest surviving logit can lie below top1)
+        const bool reuse = any_sel && top1 >= ms && !(DROP && do_drop);
         float eg = (j < E && mk) ? e_all : 0.0f;
         if (!__all_sync(kFull, reuse)) {                              // warp-uniform
-            const float m = any_sel ? fmaxf(top1, ms) : ms;
+            float m = any_sel ? fmaxf(top1, ms) : ms;
+            if (DROP && do_drop) {                                     // max over the surviving columns
+                float mm = (j < E && mk) ? l : ninf;
+#pragma unroll
+                for (int off = 8; off >= 1; off >>= 1) mm = fmaxf(mm, __shfl_xor_sync(kFull, mm, off, 16));
+                m = mm;
+            }
             const float eg2 = (j < E && mk) ? exp_D<BF16>(__fsub_rn(l, m)) : 0.0f;
             if (!reuse) eg = eg2;
         }
@@ -271,10 +293,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <bool BF16, int NDYN, int NE>
+__device__ __forceinline__ float4 ld_bf16x4_as_float(const __nv_bfloat16* p) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                       __uint_as_float(v.y & 0xffff0000u));
+}
+
+// MIXED (BF16 = false only): the fp32 gate of the training-mode forward (core.py:240-249) on a bf16 layer -- x and W_g
+// are bf16 and are widened on load, logits and all routing arithmetic are fp32, global_weight is written in bf16
+// (core.py:339).  keep [T, E] uint8 or nullptr: token_drop's capacity mask (dcmoe_drop_select).
+template <bool BF16, int NDYN, int NE, bool MIXED = false>
 __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_, const void* __restrict__ wg_,
                                                      const void* __restrict__ logits_in_,
-                                                     const int32_t* __restrict__ attn_mask, int64_t T, int H,
+                                                     const int32_t* __restrict__ attn_mask,
+                                                     const uint8_t* __restrict__ keep, int64_t T, int H,
                                                      RouteConsts rc, void* __restrict__ logits_out_,
                                                      int64_t* __restrict__ top_k, int32_t* __restrict__ expert_mask,
                                                      void* __restrict__ gw_out_, int32_t* __restrict__ block_counts,
@@ -333,8 +365,13 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
             red[warp][g + 8][8 + 2 * tq + 1] = c1[3];
         } else {
             // fp32 parity path: FFMA dot products, 2 tokens at a time, warp-reduced
-            const float* x = static_cast<const float*>(x_);
-            const float* wg = static_cast<const float*>(wg_);
+            using in_t = typename std::conditional<MIXED, __nv_bfloat16, float>::type;
+            const in_t* x = static_cast<const in_t*>(x_);
+            const in_t* wg = static_cast<const in_t*>(wg_);
+            auto ld4 = [](const in_t* p) -> float4 {
+                if constexpr (MIXED) return ld_bf16x4_as_float(p);
+                else return *reinterpret_cast<const float4*>(p);
+            };
             for (int r = 0; r < kRouterBlock; r += 2) {
                 const int64_t ra = tok0 + r, rb = ra + 1;
                 const bool va = ra < T, vb = rb < T;
@@ -342,12 +379,12 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
 #pragma unroll
                 for (int e = 0; e < kMaxDyn; ++e) acc_a[e] = acc_b[e] = 0.f;
                 for (int c = lane * 4; c < Kq; c += 128) {
-                    float4 xa = va ? *reinterpret_cast<const float4*>(x + ra * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
-                    float4 xb = vb ? *reinterpret_cast<const float4*>(x + rb * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
+                    float4 xa = va ? ld4(x + ra * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
+                    float4 xb = vb ? ld4(x + rb * (int64_t)H + k0 + c) : make_float4(0, 0, 0, 0);
 #pragma unroll
                     for (int e = 0; e < kMaxDyn; ++e) {
                         if (e < E) {
-                            float4 w = *reinterpret_cast<const float4*>(wg + (int64_t)e * H + k0 + c);
+                            float4 w = ld4(wg + (int64_t)e * H + k0 + c);
                             acc_a[e] += xa.x * w.x + xa.y * w.y + xa.z * w.z + xa.w * w.w;
                             acc_b[e] += xb.x * w.x + xb.y * w.y + xb.z * w.z + xb.w * w.w;
                         }
@@ -393,15 +430,18 @@ __global__ void __launch_bounds__(128) router_kernel(const void* __restrict__ x_
         const int am = (attn_mask != nullptr && valid) ? (attn_mask[t] != 0) : 1;
         int raw, mk;
         float gw, ga;
+        const int keep_j = (keep != nullptr && valid && j < E) ? (int)keep[t * E + j] : 1;
         // (a token past T routes a one-hot row: all-zero logits are route_token's slowest input, a nine-way tie)
-        route_token<BF16, NDYN, NE>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga);
+        route_token<BF16, NDYN, NE, true>(valid ? l : (j == 0 ? 8.0f : 0.0f), j, half, am, rc, raw, mk, gw, ga, keep_j,
+                                          keep != nullptr);
         if (valid && j < E) {
             if constexpr (BF16) {
                 ((__nv_bfloat16*)logits_out)[t * E + j] = __float2bfloat16_rn(l);
                 ((__nv_bfloat16*)gw_out)[t * E + j] = __float2bfloat16_rn(gw);
             } else {
                 ((float*)logits_out)[t * E + j] = l;
-                ((float*)gw_out)[t * E + j] = gw;
+                if constexpr (MIXED) ((__nv_bfloat16*)gw_out_)[t * E + j] = __float2bfloat16_rn(gw);   // core.py:339
+                else ((float*)gw_out)[t * E + j] = gw;
             }
             expert_mask[t * E + j] = mk;
             if (j == 0) top_k[t] = raw;
@@ -974,13 +1014,205 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Token drop, drop_policy == "probs" (core.py:305-314): per dynamic column, keep the `capacity` tokens with the largest
+// logit among the tokens that selected the expert.  One CTA per column: the selected tokens' 64-bit keys
+// (order-preserving image of the logit, then ~token so that ties go to the LOWER token index -- torch.topk leaves ties
+// to the implementation) are compacted once, then an 8-pass MSB radix select finds the capacity-th largest key; the
+// keys are unique, so exactly `capacity` tokens survive.  Integer work, exact.
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <bool LBF16>
+__global__ void __launch_bounds__(1024) drop_select_kernel(const void* __restrict__ logits_, const int32_t* __restrict__ mask,
+                                                           int64_t T, int E, long long capacity,
+                                                           unsigned long long* __restrict__ keys_all,
+                                                           uint8_t* __restrict__ keep) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_n;
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_k;
+    const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    unsigned long long* keys = keys_all + (int64_t)e * T;
+    auto key_of = [&](int64_t t) -> unsigned long long {
+        const float l = LBF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(logits_)[t * E + e])
+                              : static_cast<const float*>(logits_)[t * E + e];
+        return ((unsigned long long)ordered_bits(l) << 32) | (unsigned long long)(0xffffffffu - (unsigned)t);
+    };
+    if (tid == 0) s_n = 0u;
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < T; t0 += 1024) {
+        const int64_t t = t0 + tid;
+        const bool sel = t < T && mask[t * E + e] != 0;
+        const unsigned bal = __ballot_sync(kFull, sel);
+        unsigned base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_n, (unsigned)__popc(bal));
+        base = __shfl_sync(kFull, base, 0);
+        if (sel) keys[base + __popc(bal & ((1u << lane) - 1u))] = key_of(t);
+    }
+    __syncthreads();
+    const unsigned n = s_n;
+    unsigned long long threshold = 0ull;                  // keep every selected token
+    if ((long long)n > capacity) {
+        if (tid == 0) { s_prefix = 0ull; s_k = (unsigned long long)capacity; }
+        for (int pass = 7; pass >= 0; --pass) {
+            if (tid < 256) hist[tid] = 0u;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            for (unsigned i = tid; i < n; i += 1024) {
+                const unsigned long long k = keys[i];
+                if (pass == 7 || (k >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(unsigned)(k >> (8 * pass)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // lane q owns bins 255 - 8q .. 248 - 8q (descending): find the bin that holds the k-th largest key
+                unsigned own = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) own += hist[255 - (8 * lane + b)];
+                unsigned incl = own;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned v = __shfl_up_sync(kFull, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                const unsigned long long k = s_k;
+                const bool mine = (unsigned long long)(incl - own) < k && k <= (unsigned long long)incl;
+                if (mine) {
+                    unsigned long long rem = k - (incl - own);
+                    int bin = 255 - 8 * lane;
+                    while (rem > hist[bin]) { rem -= hist[bin]; --bin; }
+                    s_prefix = (prefix << 8) | (unsigned long long)bin;
+                    s_k = rem;
+                }
+            }
+            __syncthreads();
+        }
+        threshold = s_prefix;
+    }
+    for (int64_t t = tid; t < T; t += 1024) {
+        const bool sel = mask[t * E + e] != 0;
+        keep[t * E + e] = (sel && key_of(t) >= threshold) ? 1 : 0;
+    }
+}
+
+// shared columns of the keep mask are always 1 (core.py:313)
+__global__ void drop_fill_shared_kernel(uint8_t* __restrict__ keep, int64_t T, int n_dyn, int E) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nf = E - n_dyn;
+    if (i < T * nf) keep[(i / nf) * E + n_dyn + (i % nf)] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// aux_balance_weight branch of the load-balancing loss (core.py:380-385): weighted means over tokens.
+//   tokens_per_expert_e = sum_t float(mask[t,e]) * w_t / sum_t w_t                    (fp32 products)
+//   router_prob_e       = sum_t P(ga[t,e] * w_t) / sum_t w_t   with ga = softmax_9(logits masked with finfo.min),
+//                         products in the promoted dtype P (D for integer weights, fp32 for float weights)
+// Pass 1: half-warp per token, per-block (16 tokens) partial sums in fixed order; pass 2: one CTA, fp64, fixed order.
+template <bool BF16>
+__global__ void __launch_bounds__(256) aux_weighted_partials_kernel(const void* __restrict__ logits_, const int32_t* __restrict__ mask,
+                                                                    const float* __restrict__ w, int64_t T, int n_dyn, int E,
+                                                                    float finfo_min, int prod_bf16, float* __restrict__ partials) {
+    __shared__ float s_tok[kRouterBlock][kMaxDyn], s_prob[kRouterBlock][kMaxDyn], s_w[kRouterBlock];
+    const int tid = threadIdx.x, lane = tid & 31, half = lane >> 4, j = lane & 15;
+    const int tl = (tid >> 5) * 2 + half;
+    const int64_t t = (int64_t)blockIdx.x * kRouterBlock + tl;
+    const bool valid = t < T;
+    float l = 0.0f;
+    int mk = 0;
+    if (valid && j < n_dyn) {
+        l = BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(logits_)[t * E + j]) : static_cast<const float*>(logits_)[t * E + j];
+        mk = mask[t * E + j];
+    }
+    const float ga = softmax_lanes<BF16>(j < n_dyn ? (mk ? l : finfo_min) : __int_as_float(0xff800000), j, n_dyn);
+    const float wt = valid ? (w != nullptr ? w[t] : 1.0f) : 0.0f;      // w == nullptr: the plain means of core.py:378-379
+    float pr = __fmul_rn(ga, wt);
+    if (prod_bf16) pr = bf16_round(pr);
+    s_tok[tl][j] = (valid && j < n_dyn) ? __fmul_rn((float)mk, wt) : 0.0f;
+    s_prob[tl][j] = (valid && j < n_dyn) ? pr : 0.0f;
+    if (j == 0) s_w[tl] = wt;
+    __syncthreads();
+    if (tid < 2 * n_dyn + 1) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kRouterBlock; ++r)
+            acc = __fadd_rn(acc, tid < n_dyn ? s_tok[r][tid] : (tid < 2 * n_dyn ? s_prob[r][tid - n_dyn] : s_w[r]));
+        partials[(int64_t)blockIdx.x * 32 + tid] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(1024) aux_weighted_finish_kernel(const float* __restrict__ partials, int64_t n_blocks, int n_dyn,
+                                                                   int prob_bf16, float* __restrict__ aux_out) {
+    __shared__ double s_col[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_cols = 2 * n_dyn + 1;
+    for (int c = warp; c < n_cols; c += 32) {
+        double acc = 0.0;
+        for (int64_t b = lane; b < n_blocks; b += 32) acc += (double)partials[b * 32 + c];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+        if (lane == 0) s_col[c] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double den = s_col[2 * n_dyn];
+        double acc = 0.0;
+        for (int e = 0; e < n_dyn; ++e) {
+            const float tpe = (float)(s_col[e] / den);
+            float rp = (float)(s_col[n_dyn + e] / den);
+            if (prob_bf16) rp = bf16_round(rp);
+            acc += (double)(tpe * rp);
+        }
+        *aux_out = (float)acc * (float)n_dyn;
+    }
+}
+
 }  // namespace
 
-int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, int64_t T,
-                  const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
+int launch_drop_select(const void* logits, bool logits_bf16, const int32_t* expert_mask, int64_t T, const dcmoe_config* cfg,
+                       int64_t capacity, void* key_scratch, uint8_t* keep, cudaStream_t stream) {
+    if (T == 0) return DCMOE_OK;
+    const int n_dyn = cfg->n_real + cfg->n_null, E = n_dyn + cfg->n_fix;
+    if (T > 0x7fffffffll) {
+        set_error("dcmoe_drop_select: T must fit 31 bits");
+        return DCMOE_ERR_INVALID;
+    }
+    if (logits_bf16)
+        drop_select_kernel<true><<<n_dyn, 1024, 0, stream>>>(logits, expert_mask, T, E, (long long)capacity,
+                                                             (unsigned long long*)key_scratch, keep);
+    else
+        drop_select_kernel<false><<<n_dyn, 1024, 0, stream>>>(logits, expert_mask, T, E, (long long)capacity,
+                                                              (unsigned long long*)key_scratch, keep);
+    if (cfg->n_fix > 0)
+        drop_fill_shared_kernel<<<(unsigned)ceil_div(T * cfg->n_fix, 256), 256, 0, stream>>>(keep, T, n_dyn, E);
+    return check_cuda(cudaGetLastError(), "drop_select_kernel launch");
+}
+
+int launch_aux_weighted(const void* logits, bool arith_bf16, const int32_t* expert_mask, const float* w, bool prod_bf16,
+                        int64_t T, const dcmoe_config* cfg, float* scratch, float* aux_out, cudaStream_t stream) {
+    const int n_dyn = cfg->n_real + cfg->n_null, E = n_dyn + cfg->n_fix;
+    const int64_t n_blocks = ceil_div(T, kRouterBlock);
+    if (T == 0) return DCMOE_OK;
+    const float fmin_bf16 = -3.3895313892515355e38f, fmin_f32 = -3.4028234663852886e38f;
+    if (arith_bf16)
+        aux_weighted_partials_kernel<true><<<(unsigned)n_blocks, 256, 0, stream>>>(logits, expert_mask, w, T, n_dyn, E, fmin_bf16,
+                                                                                  prod_bf16 ? 1 : 0, scratch);
+    else
+        aux_weighted_partials_kernel<false><<<(unsigned)n_blocks, 256, 0, stream>>>(logits, expert_mask, w, T, n_dyn, E, fmin_f32, 0,
+                                                                                   scratch);
+    aux_weighted_finish_kernel<<<1, 1024, 0, stream>>>(scratch, n_blocks, n_dyn, (arith_bf16 && prod_bf16) ? 1 : 0, aux_out);
+    return check_cuda(cudaGetLastError(), "aux_weighted kernels launch");
+}
+
+int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, const uint8_t* keep,
+                  int flags, int64_t T, const dcmoe_config* cfg, void* logits_out, int64_t* top_k, int32_t* expert_mask,
                   void* global_weight, int32_t* block_counts, float* block_probs, cudaStream_t stream) {
     if (T == 0) return DCMOE_OK;
-    const bool bf16 = cfg->dtype == DCMOE_BF16;
+    // DCMOE_ROUTER_FP32_GATE on a bf16 layer: logits and routing arithmetic in fp32 (core.py:240-249)
+    const bool mixed = (flags & DCMOE_ROUTER_FP32_GATE) && cfg->dtype == DCMOE_BF16;
+    const bool bf16 = cfg->dtype == DCMOE_BF16 && !mixed;
     RouteConsts rc;
     rc.n_dyn = cfg->n_real + cfg->n_null;
     rc.E = rc.n_dyn + cfg->n_fix;
@@ -998,16 +1230,16 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
     rc.fixed_k = cfg->top_p == 0.0 ? cfg->fixed_top_k : 0;
     const int64_t n_blocks = ceil_div(T, kRouterBlock);
     dim3 grid((unsigned)n_blocks), block(128);
-#define DCMOE_LAUNCH_ROUTER(BF, ND, NE_)                                                                              \
-    router_kernel<BF, ND, NE_><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, T, cfg->hidden_size, rc, \
-                                                           logits_out, top_k, expert_mask, global_weight,            \
-                                                           block_counts, block_probs)
+#define DCMOE_LAUNCH_ROUTER(BF, ND, NE_, MX)                                                                                   \
+    router_kernel<BF, ND, NE_, MX><<<grid, block, 0, stream>>>(x, w_gate, logits_in, attn_mask, keep, T, cfg->hidden_size, rc, \
+                                                               logits_out, top_k, expert_mask, global_weight,                 \
+                                                               block_counts, block_probs)
     const bool ref_shape = rc.n_dyn == 9 && rc.E == 11;   // utils/config.json: 8 routed + 1 null + 2 shared
     const int sms = device_sm_count();
     // (decode-sized calls were measured with the one-CTA-per-block kernel too: 21.8 us vs 14.7 us for the TMA-fed
     // kernel at T = 2, so the persistent kernel is used at every size)
     const int router_smem = router_smem_bytes(cfg->hidden_size, rc.E);
-    if (bf16 && logits_in == nullptr && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
+    if (bf16 && logits_in == nullptr && keep == nullptr && cfg->hidden_size <= 2048 && cfg->hidden_size % 256 == 0 &&
         router_smem <= 232448) {
         static PerDeviceOnce attr_once;
         if (attr_once.first()) {
@@ -1058,9 +1290,11 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
         return check_cuda(cudaGetLastError(), "router_tma_kernel launch");
     }
     if (bf16) {
-        if (ref_shape) DCMOE_LAUNCH_ROUTER(true, 9, 11); else DCMOE_LAUNCH_ROUTER(true, 0, 0);
+        if (ref_shape) DCMOE_LAUNCH_ROUTER(true, 9, 11, false); else DCMOE_LAUNCH_ROUTER(true, 0, 0, false);
+    } else if (mixed) {
+        if (ref_shape) DCMOE_LAUNCH_ROUTER(false, 9, 11, true); else DCMOE_LAUNCH_ROUTER(false, 0, 0, true);
     } else {
-        if (ref_shape) DCMOE_LAUNCH_ROUTER(false, 9, 11); else DCMOE_LAUNCH_ROUTER(false, 0, 0);
+        if (ref_shape) DCMOE_LAUNCH_ROUTER(false, 9, 11, false); else DCMOE_LAUNCH_ROUTER(false, 0, 0, false);
     }
 #undef DCMOE_LAUNCH_ROUTER
     return check_cuda(cudaGetLastError(), "router_kernel launch");

@@ -132,8 +132,12 @@ class DCMoE(nn.Module):
         self.ep_size = g("ep_size", 1)
         if self.mlp_dynamic_top_p == 0 and not (1 <= int(self.mlp_dynamic_top_k or 0)):
             raise ValueError("mlp_dynamic_top_p == 0 (fixed top-k routing, core.py:256-257) needs mlp_dynamic_top_k >= 1")
-        if self.token_drop:
-            raise NotImplementedError("token_drop=True (core.py:302-329) is not implemented; utils/config.json sets it False")
+        if self.token_drop and self.drop_policy == "position":
+            # core.py:321-323 applies `cumsum(expert_mask) - 1 < capacity` to the shared experts' all-ones columns too:
+            # most tokens past the capacity lose all eleven columns and the reference returns NaN global weights and
+            # hidden states for them (tests/golden/drop_position_nan.npz) -- there is no result to be compatible with
+            raise NotImplementedError("token_drop with drop_policy='position' (core.py:321-323) yields NaN outputs in the "
+                                      "reference for tokens past the capacity; only drop_policy='probs' is implemented")
         if self.avg_hidden_states_last and self.ep_size == 1:
             raise NotImplementedError("avg_hidden_states_last=True (core.py:355-356) averages over the expert-parallel "
                                       "group and needs ep_size > 1")
@@ -236,11 +240,14 @@ class DCMoE(nn.Module):
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 aux_balance_weight: Optional[torch.Tensor] = None, router_logits: Optional[torch.Tensor] = None,
                 residual: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        if self.training:
-            raise NotImplementedError("DCMoE implements the inference forward (eval mode); training-only branches "
-                                      "(fp32 gate, jitter, gumbel routing: core.py:240-249, :111-135) are out of scope")
-        if aux_balance_weight is not None:
-            raise NotImplementedError("aux_balance_weight (core.py:380-385) is training-only and not implemented")
+        """core.py:236-358.  In ``train()`` mode this is the FORWARD of the training step only (values, no autograd
+        graph): the fp32 gate and the input jitter of core.py:240-249 run, the mixer takes its eval branch because
+        ``ignore_differentiable_router`` is set (core.py:272; utils/config.json:71)."""
+        if self.training and not self.ignore_differentiable_router:
+            raise NotImplementedError("training-mode forward with ignore_differentiable_router=False (gumbel sampling and "
+                                      "the differentiable routing function, core.py:111-135) is not implemented")
+        if self.token_drop and self.drop_policy != "probs":
+            raise ValueError(f"Invalid drop_policy: {self.drop_policy}")          # core.py:325
         if hidden_states.dim() != 3 or hidden_states.shape[-1] != self.hidden_dim:
             raise ValueError(f"hidden_states must be [batch, seq, {self.hidden_dim}]")
         if not hidden_states.is_cuda:
@@ -273,7 +280,7 @@ class DCMoE(nn.Module):
                     raise ValueError(f"ep_size ({self.ep_size}) != size of the expert-parallel group "
                                      f"({dist.get_world_size(group)})")
                 self._ep = ExpertParallelDCMoE(self, group)
-            return self._ep(hidden_states, attention_mask, None)
+            return self._ep(hidden_states, attention_mask, aux_balance_weight)
         self.pack_weights()
         return self._forward_local(hidden_states, attention_mask, aux_balance_weight, router_logits, residual,
                                    self._w13, self._w2)
@@ -306,7 +313,22 @@ class DCMoE(nn.Module):
             if not res.is_contiguous():
                 res = res.contiguous()
         impl = self.ffn_impl if self.ffn_impl is not None else (0 if dt == torch.bfloat16 else 1)
-        if (self.stage_hook is None and before_ffn is None and router_logits is None and T > 0 and
+        # ---- training-mode forward (core.py:240-249): fp32 gate, input jitter (torch's own RNG, as the reference) ----
+        gate_fp32, x_gate = False, None
+        if self.training:
+            eps_in = float(self.input_jitter_noise or 0.0)
+            if self.fp32_gate and dt != torch.float32:
+                gate_fp32 = True
+                if eps_in > 0:      # the jitter multiplies the float COPY: only the gate sees it (core.py:241-244)
+                    x_gate = x.float()
+                    x_gate *= torch.empty_like(x_gate).uniform_(1.0 - eps_in, 1.0 + eps_in)
+            elif eps_in > 0:        # in place on the caller's tensor, as core.py:244 does
+                hidden_states *= torch.empty_like(hidden_states).uniform_(1.0 - eps_in, 1.0 + eps_in)
+                x = hidden_states.reshape(T, H)
+                if not x.is_contiguous():
+                    x = x.contiguous()
+        extended = self.token_drop or aux_balance_weight is not None or gate_fp32
+        if (not extended and self.stage_hook is None and before_ffn is None and router_logits is None and T > 0 and
                 (self.use_front_small or T > 64 or dt != torch.bfloat16)):
             # the common case: the whole layer in one host call (dcmoe_forward) -- same launches as below
             logits, top_k, mask, gw, aux = ops.forward(x, wg, w13, w2, ws, out, attention_mask, res, impl)
@@ -316,15 +338,39 @@ class DCMoE(nn.Module):
                 top_k = top_k.to(torch.int32)
             return out, logits, top_k, mask, gw, aux
         hook("start")
-        small = (dt == torch.bfloat16 and 0 < T <= 64 and router_logits is None and self.use_front_small)
+        small = (dt == torch.bfloat16 and 0 < T <= 64 and router_logits is None and self.use_front_small and not extended)
+        aux_fixed = None
         if small:     # decode-sized call: router + plan + permute in one single-CTA launch
             logits, top_k, mask, gw = ops.front_small(x, wg, ws, attention_mask=attention_mask)
             hook("front_small")
         else:
-            logits, top_k, mask, gw = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask)
+            if x_gate is not None and router_logits is None:
+                # fp32 gate on the jittered float copy: fp32 x / W_g -> fp32 logits; routing then runs on those logits
+                router_logits = ops.router(x_gate, wg.float(), ws, attention_mask=attention_mask, all_fp32=True)[0]
+            logits, top_k, mask, gw = ops.router(x, wg, ws, logits_in=router_logits, attention_mask=attention_mask,
+                                                 fp32_gate=gate_fp32)
             hook("router")
             ops.plan(ws)
             hook("plan")
+            if aux_balance_weight is not None or gate_fp32:
+                # core.py:380-385 (weighted means), on the mask BEFORE any token drop (:293); with the fp32 gate the plain
+                # means are taken here too, in fp32 (the plan kernel rounds the mean probability to the layer dtype)
+                aux_fixed = ops.aux_weighted(logits, mask, aux_balance_weight, ws)
+            if self.token_drop and T > 0:
+                # core.py:302-329: capacity -> per-expert top-`capacity` tokens by logit -> AND, renormalise, new global
+                # weights; the aux loss above is the one of the un-dropped mask
+                if aux_fixed is None:
+                    aux_fixed = ws.aux_loss.clone().reshape(())
+                cap = ops.expert_capacity(self.dims, T, self.capacity_factor, self.min_capacity)
+                keep = ops.drop_select(logits, mask, cap, ws)
+                before = mask[:, : self.dims.n_dyn].sum() if self.drop_token_num_print else None
+                logits, top_k, mask, gw = ops.router(None, None, ws, logits_in=logits, attention_mask=attention_mask,
+                                                     keep=keep, fp32_gate=gate_fp32)
+                ops.plan(ws)
+                hook("token_drop")
+                if before is not None and int(__import__("os").environ.get("RANK", "0")) == 0:     # core.py:316-319 (syncs, as there)
+                    ori = int(before.item())
+                    print(f"drop {ori - int(mask[:, : self.dims.n_dyn].sum().item())} tokens from total {ori} tokens")
         if T > 0:
             if not small:
                 ops.permute(x, mask, gw, ws)
@@ -339,11 +385,15 @@ class DCMoE(nn.Module):
                 hook("ffn_gemm1")
                 ops.grouped_ffn(x, w13, w2, ws, impl, phase=2)
                 hook("ffn_gemm2")
-            aux = torch.empty((), dtype=torch.float32, device=x.device)
-            ops.combine(ws, out, res, aux_out=aux)      # the 4-byte aux copy rides in the combine launch
+            if aux_fixed is not None:
+                aux = aux_fixed
+                ops.combine(ws, out, res)
+            else:
+                aux = torch.empty((), dtype=torch.float32, device=x.device)
+                ops.combine(ws, out, res, aux_out=aux)      # the 4-byte aux copy rides in the combine launch
             hook("combine")
         else:
-            aux = ws.aux_loss.clone().reshape(())
+            aux = aux_fixed if aux_fixed is not None else ws.aux_loss.clone().reshape(())
         if ws.reduced and not torch.cuda.is_current_stream_capturing():
             ws.note_overflow_async()
         if self.mlp_dynamic_top_p == 0:

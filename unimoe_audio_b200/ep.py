@@ -691,6 +691,14 @@ class ExpertParallelDCMoE:
         path = choose_path(T, self.world, hidden_states.dtype, self.mode, self.gather_min_tokens,
                            decode_ok=(router_logits is None and self.m.stage_hook is None and aux_balance_weight is None
                                       and self.decode_applicable(T, hidden_states.dtype)))
+        if self.m.token_drop or self.m.training or aux_balance_weight is not None:
+            # the capacity branch, the training-mode gate and the weighted aux loss are per-rank computations on the
+            # rank's own tokens (core.py:293-329 runs before the exchange): they ride on the weight-gather path, which is
+            # the single-GPU forward over local tokens; the token-dispatch kernels do not carry them
+            if self.mode == "dispatch":
+                raise NotImplementedError("token_drop / training-mode forward / aux_balance_weight need the weight-gather "
+                                          "expert-parallel path (DCMOE_EP_MODE=auto or gather)")
+            path = "gather"
         if self.check_lockstep:
             self._check_lockstep(T, path)
         self.last_path = path
@@ -700,9 +708,6 @@ class ExpertParallelDCMoE:
         elif path == "gather":
             out = self.gather_forward(hidden_states, attention_mask, aux_balance_weight, router_logits)
         else:
-            if aux_balance_weight is not None:
-                raise NotImplementedError("aux_balance_weight on the token-dispatch expert-parallel path: use "
-                                          "DCMOE_EP_MODE=gather (the weighted loss is a per-rank quantity there too)")
             out = self.dispatch_forward(hidden_states, attention_mask, router_logits)
         if getattr(self.m, "avg_hidden_states_last", False):
             # core.py:355-356: all_reduce(final_hidden_states, AVG) over the expert-parallel group in eval mode

@@ -204,12 +204,19 @@ class Workspace:
 
 @guarded
 def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Workspace, logits_in: Optional[torch.Tensor] = None,
-           attention_mask: Optional[torch.Tensor] = None):
-    """Top-P router.  Returns (full_router_logits, dynamic_top_k, expert_mask, global_weight)."""
+           attention_mask: Optional[torch.Tensor] = None, keep: Optional[torch.Tensor] = None, fp32_gate: bool = False,
+           all_fp32: bool = False):
+    """Top-P router.  Returns (full_router_logits, dynamic_top_k, expert_mask, global_weight).  ``keep`` [T, E] uint8:
+    token_drop's capacity mask (``drop_select``); ``fp32_gate``: fp32 logits and routing arithmetic on a bf16 layer
+    (training-mode forward, core.py:240-249); ``all_fp32``: x / w_gate are float32 tensors and every output is float32
+    although the workspace belongs to a bf16 layer (the fp32 gate on a jittered float copy of the input)."""
     lib = _lib.load()
     dims, T, dt, dev = ws.dims, ws.T, ws.dtype, ws.device
     E = dims.n_experts
-    logits = torch.empty((T, E), dtype=dt, device=dev)
+    if all_fp32:
+        dt, fp32_gate = torch.float32, False
+    ldt = torch.float32 if fp32_gate else dt
+    logits = torch.empty((T, E), dtype=ldt, device=dev)
     top_k = torch.empty((T,), dtype=torch.int64, device=dev)
     mask = torch.empty((T, E), dtype=torch.int32, device=dev)
     gw = torch.empty((T, E), dtype=dt, device=dev)
@@ -219,12 +226,68 @@ def router(x: Optional[torch.Tensor], w_gate: Optional[torch.Tensor], ws: Worksp
         if am.numel() != T:
             raise ValueError("attention_mask must have one entry per token")
     if logits_in is not None:
-        if logits_in.shape != (T, E) or logits_in.dtype != dt or not logits_in.is_contiguous():
-            raise ValueError("logits_in must be a contiguous [T, E] tensor of the layer dtype")
-    cfg = ws.cfg
-    _lib.check(lib.dcmoe_router(_ptr(x), _ptr(w_gate), _ptr(logits_in), _ptr(am), T, cfg, _ptr(logits), _ptr(top_k),
-                                _ptr(mask), _ptr(gw), _ptr(ws.plan), _stream()), "dcmoe_router")
+        if logits_in.shape != (T, E) or logits_in.dtype != ldt or not logits_in.is_contiguous():
+            raise ValueError("logits_in must be a contiguous [T, E] tensor of the layer dtype (float32 with the fp32 gate)")
+    if keep is not None and (keep.shape != (T, E) or keep.dtype != torch.uint8 or not keep.is_contiguous()):
+        raise ValueError("keep must be a contiguous uint8 [T, E] tensor")
+    cfg = ws.cfg if dt == ws.dtype else dims.c_config(dt)
+    if keep is None and not fp32_gate:
+        _lib.check(lib.dcmoe_router(_ptr(x), _ptr(w_gate), _ptr(logits_in), _ptr(am), T, cfg, _ptr(logits), _ptr(top_k),
+                                    _ptr(mask), _ptr(gw), _ptr(ws.plan), _stream()), "dcmoe_router")
+    else:
+        _lib.check(lib.dcmoe_router_ex(_ptr(x), _ptr(w_gate), _ptr(logits_in), _ptr(am), _ptr(keep),
+                                       _lib.ROUTER_FP32_GATE if fp32_gate else 0, T, cfg, _ptr(logits), _ptr(top_k),
+                                       _ptr(mask), _ptr(gw), _ptr(ws.plan), _stream()), "dcmoe_router_ex")
     return logits, top_k, mask, gw
+
+
+def expert_capacity(dims: LayerDims, T: int, capacity_factor: float, min_capacity: int) -> int:
+    """core.py:170-175 + the clamp of :306-308 (host arithmetic, done on the C side in float32 as the reference does)."""
+    import ctypes
+
+    lib = _lib.load()
+    cap = ctypes.c_int64(0)
+    _lib.check(lib.dcmoe_expert_capacity(T, dims.c_config(torch.float32), float(capacity_factor), int(min_capacity),
+                                         ctypes.byref(cap)), "dcmoe_expert_capacity")
+    return int(cap.value)
+
+
+@guarded
+def drop_select(logits: torch.Tensor, expert_mask: torch.Tensor, capacity: int, ws: Workspace) -> torch.Tensor:
+    """Capacity mask of token_drop / "probs" (core.py:305-314): uint8 [T, E]."""
+    lib = _lib.load()
+    T, E = logits.shape
+    keep = torch.empty((T, E), dtype=torch.uint8, device=logits.device)
+    scratch = getattr(ws, "_drop_keys", None)
+    if scratch is None or scratch.numel() < ws.dims.n_dyn * max(T, 1):
+        scratch = ws._drop_keys = torch.empty(ws.dims.n_dyn * max(T, 1), dtype=torch.int64, device=logits.device)
+    _lib.check(lib.dcmoe_drop_select(_ptr(logits), _TORCH_DT[logits.dtype], _ptr(expert_mask), T, ws.cfg, int(capacity),
+                                     _ptr(scratch), _ptr(keep), _stream()), "dcmoe_drop_select")
+    return keep
+
+
+@guarded
+def aux_weighted(logits: torch.Tensor, expert_mask: torch.Tensor, aux_balance_weight: Optional[torch.Tensor], ws: Workspace) -> torch.Tensor:
+    """Load-balancing loss with aux_balance_weight (core.py:380-385; None: the plain means of :378-379 evaluated in the
+    logits' dtype): float32 0-dim tensor."""
+    lib = _lib.load()
+    T = logits.shape[0]
+    integer, w = False, None
+    if aux_balance_weight is not None:
+        if aux_balance_weight.numel() != T:
+            # core.py:381-383 broadcasts a [B, S] weight over num_hidden_layers = rows / (B * S) stacked layers; a single
+            # block call always has rows == B * S
+            raise ValueError("aux_balance_weight must have one entry per token ([batch, seq])")
+        integer = not aux_balance_weight.dtype.is_floating_point
+        w = aux_balance_weight.reshape(-1).to(device=logits.device, dtype=torch.float32).contiguous()
+    scratch = getattr(ws, "_aux_scratch", None)
+    n = (max(T, 1) + _lib.ROUTER_BLOCK - 1) // _lib.ROUTER_BLOCK * 32
+    if scratch is None or scratch.numel() < n:
+        scratch = ws._aux_scratch = torch.empty(n, dtype=torch.float32, device=logits.device)
+    aux = torch.empty((), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.dcmoe_aux_weighted(_ptr(logits), _TORCH_DT[logits.dtype], _ptr(expert_mask), _ptr(w), 1 if integer else 0,
+                                      T, ws.cfg, _ptr(scratch), _ptr(aux), _stream()), "dcmoe_aux_weighted")
+    return aux
 
 
 @guarded
