@@ -167,6 +167,11 @@ int dcmoe_drop_select(const void* logits, int logits_dtype, const int32_t* exper
 int dcmoe_aux_weighted(const void* logits, int logits_dtype, const int32_t* expert_mask, const float* weight, int integer_weights,
                        int64_t T, const dcmoe_config* cfg, float* scratch, float* aux_out, void* stream);
 
+/* Test hook: y[i] = the router's exponential of x[i].  mode 0: the production correctly rounded expf (float-pair fast
+ * path + double-precision fallback, csrc/exp_fast.cuh), 1: (float)exp((double)x) (the definition), 2: the fp32 layers'
+ * Sleef expf_u10.  tests/ compare 0 against 1 and against oracle/exp_fast.h. */
+int dcmoe_test_exp(const float* x, float* y, int64_t n, int mode, void* stream);
+
 /*
  * Plan: exact integer histogram -> exclusive prefix sums -> segment bases, tile table, aux loss.
  * Replaces core.py:455 (capacity = mask.sum(0).max(), here exact per-expert counts instead of a padded

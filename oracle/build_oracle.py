@@ -16,7 +16,8 @@ OUT = os.path.join(OUT_DIR, "libroute_oracle.so")
 
 def build(force: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= os.path.getmtime(SRC):
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(os.path.join(HERE, "exp_fast.h")))
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:
         return OUT
     # -ffp-contract=off: every rounding point in the source is a rounding point in the binary;
     # fmaf() calls still compile to hardware FMA with -mfma (and are exact in libm otherwise).

@@ -266,6 +266,9 @@ int dcmoe_oracle_route_ex(const float* logits, const int32_t* attn_mask, const u
 /* Stand-alone helpers exported for unit tests of the arithmetic spec */
 float dcmoe_oracle_exp_sleef(float x) { return exp_sleef_u10(x); }
 float dcmoe_oracle_exp_cr(float x) { return exp_cr(x); }
+/* the float-pair evaluation the CUDA router runs (oracle/exp_fast.h); *fallback = 1 when Ziv's test rejects it */
+#include "exp_fast.h"
+float dcmoe_oracle_exp_fast(float x, int* fallback) { return dcmoe_exp_fast(x, fallback, 0, 0, 0); }
 float dcmoe_oracle_bf16_round(float x) { return bf16_round(x); }
 void dcmoe_oracle_softmax(const float* v, int n, int bf16, float* out) { softmax_D(v, n, bf16, out); }
 

@@ -37,6 +37,8 @@ def lib():
         _LIB.dcmoe_oracle_exp_sleef.argtypes = [ctypes.c_float]
         _LIB.dcmoe_oracle_exp_cr.restype = ctypes.c_float
         _LIB.dcmoe_oracle_exp_cr.argtypes = [ctypes.c_float]
+        _LIB.dcmoe_oracle_exp_fast.restype = ctypes.c_float
+        _LIB.dcmoe_oracle_exp_fast.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_int)]
     return _LIB
 
 

@@ -792,3 +792,39 @@ def test_layer_on_a_device_that_is_not_current(dev):
     assert torch.cuda.current_device() == 0
     for a, b in zip(o1, o0):
         assert a.device == d1 and torch.equal(a.cpu(), b.cpu())
+
+
+def test_router_exponential_is_the_correctly_rounded_one(dev):
+    """csrc/exp_fast.cuh (float-pair evaluation + Ziv's rounding test, no FP64 on the accepted path) against the
+    definition (float)exp((double)x) on the device and against the C statement of the same arithmetic: bit-equal on
+    4M random differences of bf16 logits, on a dense sweep of (-80, 0], on the fallback triggers the exhaustive CPU run
+    found, and outside the fast domain."""
+    import ctypes
+
+    from unimoe_audio_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(11)
+    a = (torch.randn(4_000_000, generator=gen) * 1.5).to(torch.bfloat16).float()
+    b = (torch.randn(4_000_000, generator=gen) * 1.5).to(torch.bfloat16).float()
+    xs = [-(a - b).abs(), -torch.rand(2_000_000, generator=gen) * 80.0, -torch.logspace(-40, 1.9, 500_000),
+          torch.tensor([0.0, -0.0, -80.0, -79.99999, -87.0, -104.0, -200.0, 1.0, 3.5, float("-inf"), float("nan"), -1e-45, -1.17e-38])]
+    x = torch.cat(xs).to(dev).contiguous()
+    y0, y1 = torch.empty_like(x), torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.dcmoe_test_exp(x.data_ptr(), y0.data_ptr(), x.numel(), 0, st), "dcmoe_test_exp")
+    _lib.check(lib.dcmoe_test_exp(x.data_ptr(), y1.data_ptr(), x.numel(), 1, st), "dcmoe_test_exp")
+    torch.cuda.synchronize()
+    same = (y0.view(torch.int32) == y1.view(torch.int32)) | (torch.isnan(y0) & torch.isnan(y1))
+    assert bool(same.all()), x[~same][:8]
+    # the C statement (oracle/exp_fast.h) on a sample: same accept/fallback decisions are not observable, the values are
+    fb = ctypes.c_int(0)
+    xc, yc = x.cpu(), y0.cpu()
+    n_fb = 0
+    for i in range(0, xc.numel(), 4001):
+        v = R.lib().dcmoe_oracle_exp_fast(float(xc[i]), ctypes.byref(fb))
+        n_fb += fb.value
+        if not fb.value:
+            assert np.float32(v).tobytes() == np.float32(yc[i]).tobytes(), float(xc[i])
+        assert np.float32(R.lib().dcmoe_oracle_exp_cr(float(xc[i]))).tobytes() == np.float32(yc[i]).tobytes() or np.isnan(yc[i])
+    assert n_fb < 50
+

@@ -56,6 +56,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "dcmoe_router_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, POINTER(DcmoeConfig), c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dcmoe_test_exp": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "dcmoe_expert_capacity": (c_int, [c_int64, POINTER(DcmoeConfig), c_double, c_int64, POINTER(c_int64)]),
     "dcmoe_drop_select": (c_int, [c_void_p, c_int, c_void_p, c_int64, POINTER(DcmoeConfig), c_int64, c_void_p, c_void_p, c_void_p]),
     "dcmoe_aux_weighted": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, POINTER(DcmoeConfig), c_void_p, c_void_p,

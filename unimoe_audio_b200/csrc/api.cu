@@ -139,6 +139,7 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
 // launchers implemented in the other translation units
 int launch_router(const void*, const void*, const void*, const int32_t*, const uint8_t*, int, int64_t, const dcmoe_config*,
                   void*, int64_t*, int32_t*, void*, int32_t*, float*, cudaStream_t);
+int launch_exp_test(const float*, float*, int64_t, int, cudaStream_t);
 int launch_drop_select(const void*, bool, const int32_t*, int64_t, const dcmoe_config*, int64_t, void*, uint8_t*, cudaStream_t);
 int launch_aux_weighted(const void*, bool, const int32_t*, const float*, bool, int64_t, const dcmoe_config*, float*, float*,
                         cudaStream_t);
@@ -311,6 +312,13 @@ int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* p
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
     return launch_plan(T, cfg, sz, pv, (cudaStream_t)stream);
+}
+
+int dcmoe_test_exp(const float* x, float* y, int64_t n, int mode, void* stream) {
+    int rc;
+    if ((rc = require_device())) return rc;
+    if (n > 0 && (!x || !y)) { set_error("dcmoe_test_exp: NULL pointer argument"); return DCMOE_ERR_INVALID; }
+    return launch_exp_test(x, y, n, mode, (cudaStream_t)stream);
 }
 
 int dcmoe_permute(const void* x, const int32_t* expert_mask, const void* global_weight, int64_t T, int64_t row_capacity,

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "exp_fast.cuh"
 #include "ptx.cuh"
 
 namespace dcmoe {
@@ -54,8 +55,7 @@ __device__ __forceinline__ float exp_sleef_u10(float d) {
     return u;
 }
 
-// correctly rounded expf via the double-precision exp (bf16 path of ATen's softmax uses std::exp)
-__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+// exp_cr(x): correctly rounded expf (the bf16 path of ATen's softmax uses std::exp) -- exp_fast.cuh
 
 template <bool BF16>
 __device__ __forceinline__ float rnd(float v) {
@@ -1204,6 +1204,19 @@ int launch_aux_weighted(const void* logits, bool arith_bf16, const int32_t* expe
                                                                                    scratch);
     aux_weighted_finish_kernel<<<1, 1024, 0, stream>>>(scratch, n_blocks, n_dyn, (arith_bf16 && prod_bf16) ? 1 : 0, aux_out);
     return check_cuda(cudaGetLastError(), "aux_weighted kernels launch");
+}
+
+namespace {
+__global__ void exp_cr_test_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int mode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = mode == 0 ? exp_cr(x[i]) : (mode == 1 ? exp_cr_double(x[i]) : exp_sleef_u10(x[i]));
+}
+}  // namespace
+
+int launch_exp_test(const float* x, float* y, int64_t n, int mode, cudaStream_t stream) {
+    if (n <= 0) return DCMOE_OK;
+    exp_cr_test_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(x, y, n, mode);
+    return check_cuda(cudaGetLastError(), "exp_cr_test_kernel launch");
 }
 
 int launch_router(const void* x, const void* w_gate, const void* logits_in, const int32_t* attn_mask, const uint8_t* keep,
