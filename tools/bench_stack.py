@@ -1,6 +1,9 @@
 """BASELINE.json configs[2]: full decoder stack prefill (36 layers, random init), batch 16 x 4096 tokens on one B200.
 Only the MoE layers are ours; attention (torch SDPA, GQA 16/2 heads) and RMSNorm just feed realistic activations.
-Reports the summed MoE time (CUDA events around every DCMoE forward) and tokens/s through the 36 MoE layers.
+Reports the summed MoE time (CUDA events around every DCMoE forward), tokens/s through the 36 MoE layers, the per-layer
+times, the per-stage times and GEMM-1 roofline fraction of three layers (events between the kernel launches), the SM
+clocks during the run and a parity gate: layer 0's output on the first 8192 rows against the CPU oracle (routing
+bit-exact, output rtol 1e-2).
 
     python tools/bench_stack.py [--layers 36] [--batch 16] [--seq 4096]
 """
@@ -14,6 +17,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (ClockSampler, oracle_parity, load_peaks)
 from unimoe_audio_b200 import DCMoE  # noqa: E402
 
 CFG = dict(hidden_size=2048, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
@@ -44,14 +48,23 @@ def main():
         with torch.no_grad():
             for _, p in sorted(m.named_parameters(), key=lambda kv: kv[0]):
                 p.copy_((torch.randn(p.shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt))
-        m.release_reference_weights()
+        if L != 0:                      # layer 0 keeps its per-expert parameters for the parity gate
+            m.release_reference_weights()
         layers.append(m)
         attn.append({k: (torch.randn(s, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt)
                      for k, s in (("q", (2048, 2048)), ("k", (256, 2048)), ("v", (256, 2048)), ("o", (2048, 2048)))})
     B, S = a.batch, a.seq
     h0 = torch.randn(B, S, 2048, generator=torch.Generator(device=dev).manual_seed(1236), device=dev, dtype=torch.float32).to(dt)
     best = None
-    for rep in range(a.reps + 1):
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    peaks = bench.load_peaks()
+    staged = sorted({0, a.layers // 2, a.layers - 1})
+    stage_ms, parity = {}, None
+    for rep in range(a.reps + 2):
+        last = rep == a.reps + 1        # the last pass records per-stage events in three layers and checks layer 0
+        if rep == 1:
+            sampler.mark_begin()
         h = h0.clone()
         evs = []
         for L in range(a.layers):
@@ -64,23 +77,48 @@ def main():
             h = h + F.linear(o.transpose(1, 2).reshape(B, S, 2048), w["o"])
             xn = rms(h)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            hooks = []
+            if last and L in staged:
+                def hook(name, _h=hooks):
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    _h.append((name, ev))
+                layers[L].stage_hook = hook
             s.record()
             out = layers[L](xn, None, None)
             e.record()
+            layers[L].stage_hook = None
             evs.append((s, e))
+            if last and L in staged:
+                torch.cuda.synchronize()
+                ws = layers[L].last_workspace
+                rows = int(ws.mtiles[: int(ws.n_mtiles.item()), 3].sum().item())
+                st = {n1: e0.elapsed_time(e1) for (n0, e0), (n1, e1) in zip(hooks[:-1], hooks[1:])}
+                g1 = rows * bench.FLOP_PER_ROW_GEMM1 / (st["ffn_gemm1"] * 1e-3) / 1e12
+                stage_ms[f"layer{L}"] = dict(st, ffn_rows=rows, gemm1_tflops=g1, gemm1_frac_of_burst_peak=g1 / peaks["tflops_burst"],
+                                             gemm1_frac_of_sustained_peak=g1 / peaks["tflops_sustained"],
+                                             gemm2_tflops=rows * bench.FLOP_PER_ROW_GEMM2 / (st["ffn_gemm2"] * 1e-3) / 1e12)
+                if L == 0:
+                    parity = bench.oracle_parity(layers[0], xn, out, 8192)
             h = h + out[0]
         torch.cuda.synchronize()
+        if rep == a.reps:
+            sampler.mark_end()
         per_layer = [s.elapsed_time(e) for s, e in evs]
-        if rep > 0 and (best is None or sum(per_layer) < sum(best)):
+        if 0 < rep <= a.reps and (best is None or sum(per_layer) < sum(best)):
             best = per_layer
         ws = layers[-1].last_workspace
+    clocks = sampler.stop()
     T = B * S
     rows = int(ws.mtiles[: int(ws.n_mtiles.item()), 3].sum().item())
     res = {"config": f"configs[2]: {a.layers}-layer stack prefill, batch {B} x {S} tokens, bf16, 1 x B200",
            "moe_ms_total": sum(best), "moe_ms_per_layer_mean": sum(best) / len(best), "moe_ms_per_layer_min": min(best),
            "moe_ms_per_layer_max": max(best), "tokens_per_s_through_moe_layers": T * a.layers / (sum(best) * 1e-3),
            "ffn_rows_last_layer": rows, "mean_routed_experts_last_layer": (rows - T) / T,
-           "finite": bool(torch.isfinite(h.float()).all().item())}
+           "finite": bool(torch.isfinite(h.float()).all().item()),
+           "moe_ms_per_layer": best, "stages_of_layers": stage_ms, "clocks": clocks, "parity_layer0_first_8192_rows": parity,
+           "peaks": peaks, "workspace_rows": int(ws.row_capacity), "note": "best of %d timed passes; activations chained through "
+           "torch attention + RMSNorm between the MoE layers (not timed)" % a.reps}
     print(json.dumps(res))
 
 
