@@ -174,3 +174,22 @@ def test_decode_sized_expert_parallel_path_matches_single_gpu(setup, world, T, m
     ws0 = lr.ranks[0]._dws
     mt = ws0.mtiles[: int(ws0.n_mtiles.item())].cpu().tolist()
     assert {g for _a, _o, g, _n in mt} >= {8}
+
+
+@pytest.mark.parametrize("world,T", [(2, 2), (8, 8), (4, 5)])
+def test_decode_sized_calls_with_replicated_experts_match_single_gpu(setup, world, T):
+    """Decode policy "replicate" (the default of ExpertParallelDCMoE): every rank keeps a resident copy of all experts'
+    packs (fetched once) and runs its own tokens with no exchange -- rows bit-equal to the single-GPU forward."""
+    from unimoe_audio_b200.ep import LocalRanks
+    m, W, dev, dt = setup
+    gen = torch.Generator().manual_seed(7 * world + T)
+    lr = LocalRanks(m, world)
+    for _ in range(2):          # the second call reuses the resident packs
+        xs = [(torch.randn(1, T, 2048, generator=gen) * (0.5 + r % 3)).to(dt).to(dev) for r in range(world)]
+        outs = lr.resident_forward(xs)
+        torch.cuda.synchronize()
+        for r in range(world):
+            ref = m(xs[r], None, None)
+            for i in range(6):
+                assert torch.equal(outs[r][i], ref[i]), (r, i)
+    assert all(ep._resident is not None for ep in lr.ranks)

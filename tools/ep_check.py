@@ -137,8 +137,10 @@ def main():
     torch.cuda.synchronize()
     results["avg_hidden_states_last"] = torch.equal(out3[0], base_out)
 
-    # ---- decode-sized calls take the replicated-routing path: bit-equal to one GPU, inputs change every call ----
+    # ---- decode-sized calls, policy "exchange" (replicated routing of the gathered tokens): bit-equal to one GPU, inputs
+    # change every call ----
     ok = True
+    ep.decode_policy = "exchange"
     for Td in (1, 4, 64 // world, 2, 2, 2):
         xd_all, off, xd = batch([Td] * world)
         assert ep.decode_applicable(Td, dt)
@@ -159,6 +161,21 @@ def main():
         rd = m(xd_all, am_all, None)
         ok = ok and same(od, rd, off, 3)
     results["decode"] = ok
+
+    # ---- decode-sized calls, policy "replicate" (the default): resident copy of every expert's pack, no exchange per
+    # call; rows equal the single-GPU forward of the concatenated batch, the aux loss is the one of the local tokens ----
+    ep.decode_policy = "replicate"
+    ok = True
+    for Td in (2, 64 // world, 1, 2):
+        xd_all, off, xd = batch([Td] * world)
+        od = ep(xd, None, None)
+        assert ep.last_path == "decode" and ep._resident is not None
+        torch.cuda.synchronize()
+        rd = m(xd_all, None, None)
+        rl = m(xd, None, None)
+        torch.cuda.synchronize()
+        ok = ok and same(od, rd, off, Td) and torch.equal(od[5], rl[5])
+    results["decode_replicated"] = ok
 
     all_ok = all(results.values())
     print(f"rank {rank}: " + " ".join(f"{k}={'ok' if v else 'FAILED'}" for k, v in results.items()), flush=True)

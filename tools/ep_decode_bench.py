@@ -29,7 +29,10 @@ def main():
         for _, p in sorted(m.named_parameters(), key=lambda kv: kv[0]):
             p.copy_((torch.randn(p.shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(dt))
     ep = ExpertParallelDCMoE(m, dist.group.WORLD)
-    for T in (2, 16, 64):
+    cases = [(pol, T) for pol in ("replicate", "exchange") for T in (2, 64 // world)] + [("large-T paths", 16)]
+    for pol, T in cases:
+        ep.decode_policy = pol if pol != "large-T paths" else "off"
+        ep.decode_mode = ep.decode_policy != "off"
         x = torch.randn(1, T, 2048, generator=gen, device=dev, dtype=torch.float32).to(dt)
         for _ in range(10):
             ep(x, None, None)
@@ -73,7 +76,7 @@ def main():
             if rank == 0:
                 print("graph capture failed:", str(exc)[:200], flush=True)
         if rank == 0:
-            print(f"EP{world} T/rank={T:4d}: eager {t.item():8.1f} us per layer call, CUDA-graph replay {g_us:8.1f} us", flush=True)
+            print(f"EP{world} T/rank={T:4d} [{pol}, path {ep.last_path}]: eager {t.item():8.1f} us per layer call, CUDA-graph replay {g_us:8.1f} us", flush=True)
     # captured graphs hold NCCL work: skip the orderly teardown (it was seen to hang) and leave at once
     torch.cuda.synchronize()
     dist.barrier()

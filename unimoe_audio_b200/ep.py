@@ -372,7 +372,15 @@ class ExpertParallelDCMoE:
         self._side = None
         self.comm_events = []        # (name, start, end) CUDA events of the comm / copy streams, filled when a stage hook is set
         self._local_cfg = None
-        self.decode_mode = os.environ.get("DCMOE_EP_DECODE", "1") != "0"
+        # decode-sized calls (world * T <= 64): "replicate" (default) = keep a resident copy of the remote experts' packs
+        # (fetched once over NVLink, 270 MB x (R-1)/R per layer) and run the call with no per-call exchange at all;
+        # "exchange" = replicate the TOKENS instead (decode_forward); "0" = take the large-T paths.  Measured at 8 GPUs
+        # (profiles/r02_ep_decode_latency.txt): exchange 104 us per layer call against 72-85 us on one GPU -- at this size the
+        # layer is bound by per-kernel fixed costs, not by the weight bytes a rank streams, so sharding them buys nothing
+        env_d = os.environ.get("DCMOE_EP_DECODE", "replicate")
+        self.decode_policy = {"1": "exchange", "0": "off"}.get(env_d, env_d)
+        self.decode_mode = self.decode_policy != "off"
+        self._resident = None              # (w13_full, w2_full): all experts' packs, kept (decode policy "replicate")
         self._dws: Optional[EpWorkspace] = None
         self.last_path = None
         self._call = 0
@@ -666,6 +674,30 @@ class ExpertParallelDCMoE:
         ctx.slot_free[slot].record(main)
         return out
 
+    def resident_forward(self, hidden_states: torch.Tensor, attention_mask=None, aux_balance_weight=None, router_logits=None):
+        """Decode-sized calls with the experts replicated: the first call pulls every remote expert's packed weights
+        (collective once per layer: the handle exchange) into a pack that STAYS resident; every later call is the
+        single-GPU forward on this rank's tokens -- no barrier, no exchange, CUDA-graph capturable like the plain layer.
+        Inference weights are static; call ``drop_resident_weights()`` after changing them."""
+        ctx = self.context(hidden_states.dtype, hidden_states.device)
+        if self._resident is None:
+            self.pack_local_weights()
+            if self._peer_w is None:
+                self._exchange_weight_handles()
+            d = self.m.dims
+            G = d.n_real + 1
+            w13 = torch.empty((G, 2 * d.dynamic_intermediate_size, d.hidden_size), dtype=ctx.dtype, device=ctx.device)
+            w2 = torch.empty((G, d.hidden_size, d.dynamic_intermediate_size), dtype=ctx.dtype, device=ctx.device)
+            _lib.check(_lib.load().dcmoe_ep_fetch_weights(self._peer_w[0], self._peer_w[1], self.rank, self.world,
+                                                          d.c_config(ctx.dtype), w13.data_ptr(), w2.data_ptr(),
+                                                          torch.cuda.current_stream(ctx.device).cuda_stream),
+                       "dcmoe_ep_fetch_weights")
+            self._resident = (w13, w2)
+        return self.m._forward_local(hidden_states, attention_mask, aux_balance_weight, router_logits, None, *self._resident)
+
+    def drop_resident_weights(self):
+        self._resident = None
+
     # ------------------------------------------------------------------ distributed forward
     def _check_lockstep(self, T: int, path: str):
         import torch.distributed as dist
@@ -703,7 +735,9 @@ class ExpertParallelDCMoE:
             self._check_lockstep(T, path)
         self.last_path = path
         self._call += 1
-        if path == "decode":
+        if path == "decode" and self.decode_policy == "replicate":
+            out = self.resident_forward(hidden_states, attention_mask)
+        elif path == "decode":
             out = self.decode_forward(hidden_states, attention_mask)
         elif path == "gather":
             out = self.gather_forward(hidden_states, attention_mask, aux_balance_weight, router_logits)
@@ -847,6 +881,17 @@ class LocalRanks:
             logits, top_k, mask, gw = (t[r * T:(r + 1) * T] for t in ep._droute)
             outs.append((out.view(xs[r].shape), logits, top_k, mask, gw, ep._dws.aux_loss.clone().reshape(())))
         return outs
+
+    @torch.no_grad()
+    def resident_forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
+        """Decode policy "replicate": every virtual rank keeps a resident copy of all packs and runs its tokens locally."""
+        for ep in self.ranks:
+            ep.pack_local_weights()
+            ep.context(xs[0].dtype, xs[0].device)
+        for ep in self.ranks:
+            ep.set_peer_weights([q._wbuf["w13"].ptr for q in self.ranks], [q._wbuf["w2"].ptr for q in self.ranks])
+        return [ep.resident_forward(xs[r], None if attention_masks is None else attention_masks[r])
+                for r, ep in enumerate(self.ranks)]
 
     @torch.no_grad()
     def gather_forward(self, xs: Sequence[torch.Tensor], attention_masks=None):
