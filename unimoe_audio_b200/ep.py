@@ -5,9 +5,13 @@ One process per GPU.  Rank r owns routed experts [r*n_loc, (r+1)*n_loc) (core.py
 are replicated, every rank routes its own tokens.  Three paths, picked per call from the local token count T (every
 rank of the group must call in lockstep with token counts on the same side of the two thresholds):
 
-  decode    world * T <= 64 (the same T on every rank): the tokens are replicated (pushed into every rank's buffer
-            over NVLink), routed identically everywhere, each rank streams only ITS experts' weights, and the combine
-            gathers each token's routed rows from their owners' y.
+  decode    world * T <= 64.  Default policy "replicate": every rank keeps a RESIDENT copy of the remote experts' packs
+            (fetched once, 270 MB x (world-1)/world per layer) and runs its tokens like a single GPU -- no exchange per
+            call (72 us per layer call, the single-GPU latency).  Policy "exchange" (DCMOE_EP_DECODE=exchange; the same T
+            on every rank): the TOKENS are replicated (pushed into every rank's buffer over NVLink), routed identically
+            everywhere, each rank streams only ITS experts' weights, and the combine gathers each token's routed rows
+            from their owners' y -- 88 us at 2 GPUs, 104 us at 8 (two cross-GPU barriers per call): at this size the
+            layer is bound by per-kernel fixed costs, not by the weight bytes a rank streams.
   dispatch  the reference's exchange, un-padded: the permute kernel stores each selected row straight into the owner's
             packed buffer over NVLink (``ep_dispatch``), the owners run the grouped FFN on the rows they received, the
             combine kernel gathers the routed rows back with peer loads.
