@@ -80,3 +80,24 @@ def test_choose_path_thresholds():
     assert choose_path(0, 2, bf) == "dispatch"
     # every configs[3] point (64 x 4096 tokens over 2 / 4 / 8 ranks) is a weight-gather call
     assert all(choose_path(64 * 4096 // r, r, bf) == "gather" for r in (2, 4, 8))
+
+
+def test_decode_policy_and_extended_branches_choose_their_paths(monkeypatch):
+    """Host logic of ExpertParallelDCMoE that needs no GPU: the decode policy read from DCMOE_EP_DECODE (default: a resident
+    replica of the remote experts, "exchange" = replicated tokens, "0" = off), and the launch count bench.py reports."""
+    from unimoe_audio_b200 import DCMoE
+    from unimoe_audio_b200.ep import ExpertParallelDCMoE
+    cfg = dict(hidden_size=2048, mlp_dynamic_expert_num=8, mlp_dynamic_null_expert_num=1, mlp_dynamic_top_p=0.7,
+               mlp_dynamic_top_k=0.0, mlp_fixed_expert_num=2, dynamic_intermediate_size=2752,
+               shared_intermediate_size=1376, router_jitter_noise=0.01)
+    with torch.device("meta"):
+        m = DCMoE(cfg)
+    for env, policy, on in ((None, "replicate", True), ("exchange", "exchange", True), ("1", "exchange", True), ("0", "off", False)):
+        if env is None:
+            monkeypatch.delenv("DCMOE_EP_DECODE", raising=False)
+        else:
+            monkeypatch.setenv("DCMOE_EP_DECODE", env)
+        ep = ExpertParallelDCMoE(m, group=None, rank=1, world=4)
+        assert ep.decode_policy == policy and ep.decode_mode is on and ep.n_loc == 2
+    with pytest.raises(ValueError):
+        ExpertParallelDCMoE(m, group=None, rank=0, world=3)                 # 8 experts over 3 ranks (core.py:505)

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from oracle import dcmoe_oracle as O
+from oracle import route_oracle_c as R
 
 pytestmark = pytest.mark.gpu
 
@@ -193,3 +194,36 @@ def test_decode_sized_calls_with_replicated_experts_match_single_gpu(setup, worl
             for i in range(6):
                 assert torch.equal(outs[r][i], ref[i]), (r, i)
     assert all(ep._resident is not None for ep in lr.ranks)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_training_recipe_branches_ride_on_the_weight_gather_path(setup, world):
+    """token_drop / aux_balance_weight under expert parallelism (V2 recipe: ep_size > 1 with token_drop, training.sh:55-59):
+    per-rank computations on the rank's own tokens (core.py:293-329 runs before the exchange), so every rank's result
+    must equal the single-GPU layer called on that rank's tokens alone -- all six fields, the aux loss included."""
+    from unimoe_audio_b200 import DCMoE
+    from unimoe_audio_b200.ep import LocalRanks
+    m, W, dev, dt = setup
+    with torch.device("meta"):
+        md = DCMoE(dict(O.DEFAULT_CONFIG, token_drop=True, drop_policy="probs", capacity_factor=1.0, min_capacity=8))
+    md = md.to(dt).to_empty(device=dev).eval()
+    md.load_state_dict({k: v.to(dev) for k, v in W.items()})
+    lr = LocalRanks(md, world)
+    gen = torch.Generator().manual_seed(31 + world)
+    tokens = [300, 200, 150, 90][:world]
+    xs = [torch.randn(1, t, 2048, generator=gen).to(dt).to(dev) for t in tokens]
+    ws = [torch.randint(1, 4, (1, t), generator=gen).to(dev) for t in tokens]
+    for ep in lr.ranks:
+        ep.pack_local_weights()
+        ep.context(dt, dev)
+    for ep in lr.ranks:
+        ep.set_peer_weights([q._wbuf["w13"].ptr for q in lr.ranks], [q._wbuf["w2"].ptr for q in lr.ranks])
+    for r, ep in enumerate(lr.ranks):
+        out = ep.gather_forward(xs[r], None, ws[r])
+        torch.cuda.synchronize()
+        ref = md(xs[r], None, ws[r])
+        torch.cuda.synchronize()
+        for i in range(6):
+            assert torch.equal(out[i], ref[i]), (r, i)
+        plain = R.route(ref[1].cpu())[1]
+        assert int(ref[3][:, :9].sum()) < int(plain[:, :9].sum())         # the capacity did drop something
