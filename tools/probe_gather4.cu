@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 __global__ void probe(const __grid_constant__ CUtensorMap tm, int r0, int r1, int r2, int r3, int col, uint32_t expect, uint16_t* out,
@@ -43,7 +44,7 @@ __device__ __forceinline__ uint32_t try_wait(uint32_t bar, uint32_t parity) {
     return done;
 }
 __global__ void __launch_bounds__(64) rate_kernel(const __grid_constant__ CUtensorMap tm_row, const __grid_constant__ CUtensorMap tm_box,
-                                                  const int* __restrict__ rows, int n_tiles, int stages, int gather, long long* cycles) {
+                                                  const int* __restrict__ rows, int n_tiles, int stages, int gather, long long* cycles, int n_rows) {
     extern __shared__ __align__(1024) uint8_t sm_raw[];
     __shared__ uint64_t bars[32];
     const uint32_t base = ((uint32_t)__cvta_generic_to_shared(sm_raw) + 1023u) & ~1023u;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(64) rate_kernel(const __grid_constant__ CUtens
                                  ::"r"(dst + lane * 512), "l"((uint64_t)&tm_row), "r"(kb * 64), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w), "r"(b0 + 8 * s) : "memory");
                 else if (lane == 0)
                     asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(dst), "l"((uint64_t)&tm_box), "r"(kb * 64), "r"(tile * 128), "r"(b0 + 8 * s) : "memory");
+                                 ::"r"(dst), "l"((uint64_t)&tm_box), "r"(kb * 64), "r"((tile * 128) % n_rows), "r"(b0 + 8 * s) : "memory");
                 __syncwarp();
             } else {
                 while (!try_wait(b0 + 8 * s, ph)) {}
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(64) rate_kernel(const __grid_constant__ CUtens
     if (threadIdx.x == 0) cycles[blockIdx.x] = clock64() - t0;
 }
 
-static void rate_probe() {
-    const int64_t R = 65536, C = 2048;        // a [65536, 2048] bf16 activation matrix: 256 MiB
+static void rate_probe(int64_t R) {
+    const int64_t C = 2048;                   // a [R, 2048] bf16 activation matrix (65536 rows = 256 MiB; 8192 = 32 MiB, L2 resident)
     uint16_t* x;
     cudaMalloc(&x, R * C * 2);
     cudaMemset(x, 0, R * C * 2);
@@ -112,9 +113,9 @@ static void rate_probe() {
     for (int gather : {0, 1}) {
         for (int stages : {2, 4, 8}) {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-            rate_kernel<<<148, 64, 8 * 16384 + 1024>>>(tm_row, tm_box, drows, n_tiles, stages, gather, dcyc);
+            rate_kernel<<<148, 64, 8 * 16384 + 1024>>>(tm_row, tm_box, drows, n_tiles, stages, gather, dcyc, (int)R);
             cudaEventRecord(e0);
-            rate_kernel<<<148, 64, 8 * 16384 + 1024>>>(tm_row, tm_box, drows, n_tiles, stages, gather, dcyc);
+            rate_kernel<<<148, 64, 8 * 16384 + 1024>>>(tm_row, tm_box, drows, n_tiles, stages, gather, dcyc, (int)R);
             cudaEventRecord(e1);
             cudaError_t err = cudaDeviceSynchronize();
             float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -122,8 +123,8 @@ static void rate_probe() {
             cudaMemcpy(cyc.data(), dcyc, 148 * 8, cudaMemcpyDeviceToHost);
             long long mx = 0; for (auto c : cyc) mx = c > mx ? c : mx;
             const double bytes = (double)n_tiles * 32 * 16384;
-            printf("%s, ring of %d x 16 KB: %s  %.3f ms  %.2f TB/s into shared memory, %.0f cycles per 16 KB stage per SM\n",
-                   gather ? "32 x gather4 (random rows)" : "1 x 128-row box (contiguous)", stages, cudaGetErrorString(err), ms,
+            printf("[%lld source rows] %s, ring of %d x 16 KB: %s  %.3f ms  %.2f TB/s into shared memory, %.0f cycles per 16 KB stage per SM\n",
+                   (long long)R, gather ? "32 x gather4 (random rows)" : "1 x 128-row box (contiguous)", stages, cudaGetErrorString(err), ms,
                    bytes / (ms * 1e-3) / 1e12, (double)mx / (8.0 * 32));
         }
     }
@@ -132,7 +133,7 @@ static void rate_probe() {
 int main(int argc, char** argv) {
     cuInit(0);
     cudaSetDevice(0);
-    if (argc > 1) { rate_probe(); return 0; }
+    if (argc > 1) { rate_probe(argc > 2 ? atoll(argv[2]) : 65536); return 0; }
     const int R = 64, C = 256;
     std::vector<uint16_t> h(R * C);
     for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) h[r * C + c] = (uint16_t)(r * 256 + c);
