@@ -88,7 +88,11 @@ typedef struct dcmoe_plan_layout {
     int64_t mtiles;         /* [max_mtiles] dcmoe_mtile                                          */
     int64_t overflow;       /* [1] int32                 1 if the rows did not fit row_capacity (tiles dropped!)  */
     int64_t total;          /* == plan_bytes */
+    int64_t small_tokens;   /* [DCMOE_SMALL_ROWS] int32  decode-sized calls (dcmoe_front_small): token of every routed row of   */
+                            /*                           row space -- the weight-streaming GEMM-1 gathers its token rows        */
+                            /*                           straight from x with TMA gather4 (T <= 32), x_packed is not read       */
 } dcmoe_plan_layout;
+#define DCMOE_SMALL_ROWS 2176   /* 128 + 16 x 128: row space of a call with T <= 64 tokens */
 
 typedef struct dcmoe_mtile {
     int32_t a_row;     /* GEMM-1 A row: in x (group == n_real) or in x_packed (routed)  */

@@ -38,7 +38,7 @@ class DcmoeSizes(Structure):
 
 class DcmoePlanLayout(Structure):
     _fields_ = [(n, c_int64) for n in ("block_counts", "block_probs", "block_offsets", "counts", "seg_base",
-                                       "n_mtiles", "aux_loss", "mtiles", "overflow", "total")]
+                                       "n_mtiles", "aux_loss", "mtiles", "overflow", "total", "small_tokens")]
 
 
 class DcmoeError(RuntimeError):

@@ -131,6 +131,7 @@ static int fill_sizes(const dcmoe_config* cfg, int64_t T, int64_t row_capacity_h
     l->aux_loss = off;     off = align_up(off + 4, 16);
     l->mtiles = off;       off = align_up(off + sz->max_mtiles * (int64_t)sizeof(dcmoe_mtile), 16);
     l->overflow = off;     off = align_up(off + 4, 16);
+    l->small_tokens = off; off = align_up(off + DCMOE_SMALL_ROWS * 4, 16);
     l->total = off;
     sz->plan_bytes = off;
     return DCMOE_OK;
@@ -145,7 +146,8 @@ int launch_aux_weighted(const void*, bool, const int32_t*, const float*, bool, i
                         cudaStream_t);
 int launch_plan(int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView, cudaStream_t);
 int launch_front_small(const void*, const void*, const int32_t*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
-                       void*, int64_t*, int32_t*, void*, void*, int32_t*, int32_t*, float*, cudaStream_t);
+                       void*, int64_t*, int32_t*, void*, void*, int32_t*, int32_t*, float*, bool, cudaStream_t);
+bool ffn_stream_gathers_from_x(int64_t T);
 int launch_permute(const void*, const int32_t*, const void*, int64_t, const dcmoe_config*, const dcmoe_sizes&, PlanView,
                    void*, int32_t*, int32_t*, float*, cudaStream_t);
 int launch_combine(const void*, const int32_t*, int64_t, const dcmoe_config*, const void*, void*, const float*, float*,
@@ -303,7 +305,7 @@ int dcmoe_front_small(const void* x, const void* w_gate, const int32_t* attn_mas
     dcmoe_sizes sz; PlanView pv;
     if ((rc = plan_for(cfg, T, row_capacity, plan, &sz, &pv))) return rc;
     return launch_front_small(x, w_gate, attn_mask, T, cfg, sz, pv, logits_out, top_k, expert_mask, global_weight, x_packed,
-                              slot_of, row_token, row_scale, (cudaStream_t)stream);
+                              slot_of, row_token, row_scale, true, (cudaStream_t)stream);
 }
 
 int dcmoe_plan(int64_t T, int64_t row_capacity, const dcmoe_config* cfg, void* plan, void* stream) {
@@ -405,8 +407,22 @@ int dcmoe_forward(const void* x, const void* w_gate, const int32_t* attn_mask, c
     int rc;
     const bool small = cfg && cfg->dtype == DCMOE_BF16 && T > 0 && T <= 64;
     if (small) {
-        if ((rc = dcmoe_front_small(x, w_gate, attn_mask, T, row_capacity, cfg, logits_out, top_k, expert_mask, global_weight,
-                                    ws->plan, ws->x_packed, ws->slot_of, ws->row_token, ws->row_scale, stream)))
+        // x_packed is only filled when the FFN that follows reads it: the weight-streaming GEMM-1 gathers its token rows
+        // straight from x (T <= 32)
+        dcmoe_sizes szf; PlanView pvf;
+        if ((rc = validate_config(cfg))) return rc;
+        if ((rc = require_device())) return rc;
+        if (!x || !w_gate || !logits_out || !top_k || !expert_mask || !global_weight || !ws->plan || !ws->x_packed || !ws->slot_of ||
+            !ws->row_token || !ws->row_scale) {
+            set_error("dcmoe_forward: NULL pointer argument");
+            return DCMOE_ERR_INVALID;
+        }
+        if ((rc = plan_for(cfg, T, row_capacity, ws->plan, &szf, &pvf))) return rc;
+        const char* e = getenv("DCMOE_FFN_STREAM");
+        const bool stream_ffn = impl == 0 && !(e && e[0] == '0') && ffn_stream_applicable(T, cfg, szf, 0, 0);
+        if ((rc = launch_front_small(x, w_gate, attn_mask, T, cfg, szf, pvf, logits_out, top_k, expert_mask, global_weight,
+                                     ws->x_packed, ws->slot_of, ws->row_token, ws->row_scale,
+                                     !(stream_ffn && ffn_stream_gathers_from_x(T)), (cudaStream_t)stream)))
             return rc;
     } else {
         if ((rc = dcmoe_router(x, w_gate, nullptr, attn_mask, T, cfg, logits_out, top_k, expert_mask, global_weight, ws->plan,

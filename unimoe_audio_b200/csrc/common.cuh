@@ -80,6 +80,7 @@ struct PlanView {
     float* aux_loss;
     dcmoe_mtile* mtiles;
     int32_t* overflow;
+    int32_t* small_tokens;
 };
 
 inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
@@ -94,6 +95,7 @@ inline PlanView plan_view(void* plan, const dcmoe_plan_layout& l) {
     v.aux_loss = reinterpret_cast<float*>(p + l.aux_loss);
     v.mtiles = reinterpret_cast<dcmoe_mtile*>(p + l.mtiles);
     v.overflow = reinterpret_cast<int32_t*>(p + l.overflow);
+    v.small_tokens = reinterpret_cast<int32_t*>(p + l.small_tokens);
     return v;
 }
 

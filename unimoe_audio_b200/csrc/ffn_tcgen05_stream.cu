@@ -93,6 +93,8 @@ struct StreamParams {
     int ep_base;        // them as weight groups 0..ep_n_loc-1 (+ the shared pair as group ep_n_loc); 0 = all groups local
     int ksplit;         // GEMM-2 only: 1 = the four k16 steps of a stage go to four accumulators (summed in the epilogue)
     unsigned long long* dbg;   // tuning (DCMOE_FFN_STREAM_DEBUG=1): per-CTA cycle counters, else nullptr
+    const int32_t* small_tokens;   // GEMM-1, n_tok <= 32: token of every routed row (plan.small_tokens) -> the token box of a
+                                   // routed m-tile is gathered from x with TMA gather4 (4 rows per instruction); else nullptr
 };
 
 // One segment per CTA: the CTAs are dealt to the m-tiles (= hit weight groups) as evenly as possible and the CTAs of
@@ -131,7 +133,9 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
                   const __grid_constant__ CUtensorMap tmap_a1,   // GEMM-1: x_packed   GEMM-2: h
                   const __grid_constant__ CUtensorMap tmap_b16,  // W13 / W2, boxes of 16 / 32 / 64 / 128 rows
                   const __grid_constant__ CUtensorMap tmap_b32, const __grid_constant__ CUtensorMap tmap_b64,
-                  const __grid_constant__ CUtensorMap tmap_b128, const StreamParams p) {
+                  const __grid_constant__ CUtensorMap tmap_b128,
+                  const __grid_constant__ CUtensorMap tmap_xrow,   // GEMM-1: x with a box of one row (gather4)
+                  const StreamParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + RING_BYTES + SLACK_BYTES;
@@ -148,6 +152,7 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
         prefetch_tmap(&tmap_b32);
         prefetch_tmap(&tmap_b64);
         prefetch_tmap(&tmap_b128);
+        prefetch_tmap(&tmap_xrow);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -201,6 +206,19 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
         const dcmoe_mtile mt = p.mtiles[sg.m];
         const CUtensorMap* amap = SWIGLU ? (mt.group == p.n_real ? &tmap_a0 : &tmap_a1) : &tmap_a0;
         const int a_row = SWIGLU ? mt.a_row : mt.out_row;
+        // GEMM-1, routed tile, <= 32 token rows: lane j gathers rows 4j .. 4j+3 of the token box from x (one
+        // cp.async.bulk.tensor gather4 = 4 rows x 128 B, the same swizzled layout a row box produces; ~69 cycles of TMA
+        // issue each, profiles/r02_probe_gather4.txt -- affordable for 4 - 8 per ~2000-cycle stage) instead of reading
+        // a packed copy: the front end then skips the row gather.  Rows past mt.rows gather token 0 (never stored).
+        const bool gather_a = SWIGLU && p.small_tokens != nullptr && mt.group != p.n_real;
+        int tok[4] = {0, 0, 0, 0};
+        if (gather_a && lane * 4 < p.n_tok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = lane * 4 + q;
+                tok[q] = r < mt.rows ? p.small_tokens[mt.out_row + r] : 0;
+            }
+        }
         // The B tile of a stage is nb granule slots of 16 rows x 128 B.  Runs of consecutive weight rows are fetched
         // with the largest boxes that tile them (16 / 32 / 64 / 128 rows): issuing a TMA box costs ~50 cycles
         // whatever its size, and at one box per granule that issue rate, not HBM, bounds the kernel.  Lane 0 builds
@@ -261,9 +279,11 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
             const uint32_t dst = smem_base + stage * p.stage_bytes;
             if (lane == 0) {
                 mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_alloc + nb * BOX_BYTES));
-                tma_load_2d(dst, amap, kb * BK, a_row, full_bar(stage));
+                if (!gather_a) tma_load_2d(dst, amap, kb * BK, a_row, full_bar(stage));
             }
             __syncwarp();
+            if (gather_a && lane * 4 < p.n_tok)
+                tma_gather4_2d(dst + lane * 512, &tmap_xrow, kb * BK, tok[0], tok[1], tok[2], tok[3], full_bar(stage));
             if (lane < n_box) tma_load_2d(dst + p.a_alloc + b_off, bmap, kb * BK, b_row, full_bar(stage));
             if (p.dbg) {
                 d_wait += t1 - t0;
@@ -393,6 +413,12 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
 
 }  // namespace
 
+// GEMM-1 gathers its routed token rows straight from x (TMA gather4) when the token box has at most 32 rows
+bool ffn_stream_gathers_from_x(int64_t T) {
+    static const bool on = !(getenv("DCMOE_FFN_STREAM_GATHER") && getenv("DCMOE_FFN_STREAM_GATHER")[0] == '0');
+    return on && T > 0 && T <= 32;
+}
+
 bool ffn_stream_applicable(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, int max_ctas, int ep_n_loc) {
     // every m-tile must be a whole weight group with at most 64 rows: T <= 64 (one shared tile, one tile per hit
     // expert), and the widest segment a CTA can get must fit the two accumulators / 32 producer lanes
@@ -430,12 +456,13 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
         if (rc) { attr_once.reset_current(); return rc; }
     }
     const int a_box = T <= 16 ? 16 : (T <= 32 ? 32 : 64);
-    CUtensorMap m_x, m_xp, m_h, m_w13[4], m_w2[4];
+    CUtensorMap m_x, m_xp, m_h, m_xrow, m_w13[4], m_w2[4];
     int rc;
     const int64_t packed_rows = row_capacity - sz.t_pad;
     if ((rc = make_tensor_map_bf16(&m_x, x, T, H, a_box))) return rc;
     if ((rc = make_tensor_map_bf16(&m_xp, x_packed, packed_rows > 0 ? packed_rows : 1, H, a_box))) return rc;
     if ((rc = make_tensor_map_bf16(&m_h, h, row_capacity, Id, a_box))) return rc;
+    if ((rc = make_tensor_map_bf16(&m_xrow, x, T, H, 1))) return rc;
     for (int i = 0; i < 4; ++i) {
         if ((rc = make_tensor_map_bf16(&m_w13[i], w13, (int64_t)G * 2 * Id, H, GR << i))) return rc;
         if ((rc = make_tensor_map_bf16(&m_w2[i], w2, (int64_t)G * H, Id, GR << i))) return rc;
@@ -471,6 +498,8 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     p2.out = static_cast<__nv_bfloat16*>(y);
     p2.ld_out = H;
     p1.ksplit = 0;
+    p1.small_tokens = ffn_stream_gathers_from_x(T) ? pv.small_tokens : nullptr;
+    p2.small_tokens = nullptr;
     p1.ep_n_loc = p2.ep_n_loc = ep_n_loc;
     p1.ep_base = p2.ep_base = ep_rank * ep_n_loc;
     {
@@ -490,13 +519,13 @@ int launch_ffn_tcgen05_stream(const void* x, const void* x_packed, const void* w
     dim3 grid((unsigned)n_ctas), block(NUM_THREADS);
     if (phase != 2) {
         if ((rc = check_cuda(launch_kernel(ffn_stream_kernel<true>, grid, block, SMEM_BYTES, stream, pdl_enabled(), m_x, m_xp,
-                                           m_w13[0], m_w13[1], m_w13[2], m_w13[3], p1),
+                                           m_w13[0], m_w13[1], m_w13[2], m_w13[3], m_xrow, p1),
                              "ffn_stream_kernel<SwiGLU> launch")))
             return rc;
     }
     if (phase != 1 &&
         (rc = check_cuda(launch_kernel(ffn_stream_kernel<false>, grid, block, SMEM_BYTES, stream, pdl_enabled(), m_h, m_h,
-                                       m_w2[0], m_w2[1], m_w2[2], m_w2[3], p2),
+                                       m_w2[0], m_w2[1], m_w2[2], m_w2[3], m_xrow, p2),
                          "ffn_stream_kernel<down> launch")))
         return rc;
     if (debug) {   // tuning only: synchronises

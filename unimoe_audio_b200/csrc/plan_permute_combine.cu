@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(128) permute_kernel(const char* __restrict__ x
                 slot = -1;     // row_capacity below the worst case and exceeded: the row is dropped (plan.overflow = 1)
             } else {
                 row_token[slot] = (int32_t)t;
+                if (T <= 64 && slot < DCMOE_SMALL_ROWS) pv.small_tokens[slot] = (int32_t)t;   // decode-sized: GEMM-1 gathers from x
                 const float w = load_gw(t, e);
                 row_scale[2 * (int64_t)slot] = w;
                 row_scale[2 * (int64_t)slot + 1] = w;

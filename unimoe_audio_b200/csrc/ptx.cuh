@@ -66,6 +66,15 @@ __device__ __forceinline__ void tma_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// four arbitrary rows of a 2-D tensor (tensor map with a box of {cols, 1}) -> four consecutive rows of shared memory
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3,
+                                               uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

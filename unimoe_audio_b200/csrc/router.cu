@@ -876,32 +876,48 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
     if (rc.dbg && tid == 64) rc.dbg[11] = clock64() - t_fs0;
     __syncthreads();
     if (rc.dbg && tid == 0) rc.dbg[6] = clock64() - t_fs0;
-    if (tid == 0) {
+    if (tid < 32) {
+        // segment bases and the tile table: lane e lays out expert e (exclusive warp scan of the experts' tile counts);
+        // the shared-expert tiles come first
         const int n_sh = t_pad / kTileM;
-        int row = t_pad, tile = 0;
-        for (int i = 0; i < n_sh && tile < max_mtiles; ++i, ++tile) {
+        const int cnt = tid < n_real ? s_cnt[tid] : 0;
+        const int nt = (cnt + kTileM - 1) / kTileM;
+        int incl = nt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(kFull, incl, off);
+            if (tid >= off) incl += o;
+        }
+        const int excl = incl - nt;
+        const int total_routed = __shfl_sync(kFull, incl, 31);
+        if (tid < n_real) {
+            const int row = t_pad + excl * kTileM;
+            s_seg[tid] = row;
+            pv.seg_base[tid] = row;
+            for (int i = 0; i < nt; ++i) {
+                const int tile = n_sh + excl + i;
+                if (tile < max_mtiles) {
+                    dcmoe_mtile mt;
+                    mt.out_row = row + i * kTileM; mt.a_row = mt.out_row - t_pad; mt.group = tid;
+                    mt.rows = min(kTileM, cnt - i * kTileM);
+                    pv.mtiles[tile] = mt;
+                }
+            }
+        }
+        for (int i = tid; i < n_sh && i < max_mtiles; i += 32) {
             dcmoe_mtile mt;
             mt.a_row = i * kTileM; mt.out_row = i * kTileM; mt.group = n_real;
             mt.rows = min(kTileM, T - i * kTileM);
-            pv.mtiles[tile] = mt;
+            pv.mtiles[i] = mt;
         }
-        for (int e = 0; e < n_real; ++e) {
-            s_seg[e] = row;
-            pv.seg_base[e] = row;
-            const int nt = (s_cnt[e] + kTileM - 1) / kTileM;
-            for (int i = 0; i < nt && tile < max_mtiles; ++i, ++tile) {
-                dcmoe_mtile mt;
-                mt.out_row = row + i * kTileM; mt.a_row = mt.out_row - t_pad; mt.group = e;
-                mt.rows = min(kTileM, s_cnt[e] - i * kTileM);
-                pv.mtiles[tile] = mt;
-            }
-            row += nt * kTileM;
+        if (tid == 0) {
+            const int end_row = t_pad + total_routed * kTileM;
+            s_seg[n_real] = end_row;
+            pv.seg_base[n_real] = end_row;
+            *pv.n_mtiles = min(n_sh + total_routed, max_mtiles);
+            *pv.overflow = (end_row > max_mtiles * kTileM) ? 1 : 0;
+            if (rc.dbg) rc.dbg[7] = clock64() - t_fs0;
         }
-        s_seg[n_real] = row;
-        pv.seg_base[n_real] = row;
-        *pv.n_mtiles = tile;
-        *pv.overflow = (row > max_mtiles * kTileM) ? 1 : 0;
-        if (rc.dbg) rc.dbg[7] = clock64() - t_fs0;
     }
     if (tid >= 32 && tid < 32 + n_dyn) {
         // aux loss, same reduction shape as router + plan kernels: fp32 partials per block of 16 tokens, then fp64
@@ -943,6 +959,7 @@ front_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
                 slot = -1;     // row_capacity below the worst case and exceeded: dropped (plan.overflow = 1)
             } else {
                 row_token[slot] = t;
+                if (slot < DCMOE_SMALL_ROWS) pv.small_tokens[slot] = t;   // (the weight-streaming GEMM-1 gathers its rows from x)
                 row_scale[2 * (int64_t)slot] = s_gw[t][e];
                 row_scale[2 * (int64_t)slot + 1] = s_gw[t][e];
             }
@@ -1316,7 +1333,9 @@ int launch_router(const void* x, const void* w_gate, const void* logits_in, cons
 int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_mask, int64_t T, const dcmoe_config* cfg,
                        const dcmoe_sizes& sz, PlanView pv, void* logits_out, int64_t* top_k, int32_t* expert_mask,
                        void* global_weight, void* x_packed, int32_t* slot_of, int32_t* row_token, float* row_scale,
-                       cudaStream_t stream) {
+                       bool gather_rows, cudaStream_t stream) {
+    // gather_rows == false: x_packed is not filled -- the caller's GEMM-1 gathers its token rows from x (TMA gather4,
+    // dcmoe_forward with T <= 32)
     if (T == 0) return DCMOE_OK;
     if (cfg->dtype != DCMOE_BF16 || T > kFrontMaxT) {
         set_error("dcmoe_front_small: bf16 and T <= %d only", kFrontMaxT);
@@ -1336,7 +1355,7 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
     const dim3 grid(1), block(1024);
     cudaError_t err;
     void* const x_packed_all = x_packed;
-    if (T > 16) x_packed = nullptr;     // rows are gathered by gather_rows_kernel below
+    if (T > 16 || !gather_rows) x_packed = nullptr;     // rows are gathered by gather_rows_kernel below / by the GEMM
     static unsigned long long* dbg = nullptr;
     const bool debug = getenv("DCMOE_ROUTER_DEBUG") != nullptr;
     if (debug) {
@@ -1363,7 +1382,7 @@ int launch_front_small(const void* x, const void* w_gate, const int32_t* attn_ma
             fprintf(stderr, "front_small T=%lld: gate done@%llu routing done@%llu plan done@%llu slots visible@%llu rows gathered@%llu | counts@%llu tile table@%llu aux@%llu | loop@%llu store@%llu warp2 at barrier@%llu (cycles)\n",
                     (long long)T, h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
     }
-    if (err == cudaSuccess && T > 16) {
+    if (err == cudaSuccess && T > 16 && gather_rows) {
         const int n_pairs = (int)T * cfg->n_real;
         err = launch_kernel(gather_rows_kernel, dim3((unsigned)ceil_div(n_pairs, 8)), dim3(256), 0, stream, pdl_enabled(),
                             (const __nv_bfloat16*)x, (const int32_t*)slot_of, n_pairs, cfg->n_real, cfg->hidden_size,
