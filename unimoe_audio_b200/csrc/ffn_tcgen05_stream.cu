@@ -178,14 +178,20 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
     // ones whose weights this rank holds -- its routed experts and the shared pair
     __shared__ int s_local_m[kMaxDyn + 1];
     __shared__ int s_n_local;
-    if (threadIdx.x == 0) {
-        const int n_m = min(*p.n_mtiles, kMaxDyn + 1);
-        int k = 0;
-        for (int m = 0; m < n_m; ++m) {
-            const int g = p.mtiles[m].group;
-            if (p.ep_n_loc == 0 || g == p.n_real || (g >= p.ep_base && g < p.ep_base + p.ep_n_loc)) s_local_m[k++] = m;
-        }
-        s_n_local = k;
+    __shared__ dcmoe_mtile s_mt[kMaxDyn + 1];
+    if (warp == 3) {
+        // ONE round trip for the whole plan of a decode-sized call (<= 17 m-tiles + their count): the former
+        // count -> groups -> own tile chain of dependent loads cost ~1 us at the head of each GEMM
+        const int n_all = *p.n_mtiles;
+        dcmoe_mtile mine = dcmoe_mtile{0, 0, 0, 0};
+        if (lane <= kMaxDyn) mine = p.mtiles[lane];
+        const int n_m = min(n_all, kMaxDyn + 1);
+        const bool local = lane < n_m && (p.ep_n_loc == 0 || mine.group == p.n_real ||
+                                         (mine.group >= p.ep_base && mine.group < p.ep_base + p.ep_n_loc));
+        const unsigned bal = __ballot_sync(0xffffffffu, local);
+        if (lane <= kMaxDyn) s_mt[lane] = mine;
+        if (local) s_local_m[__popc(bal & ((1u << lane) - 1u))] = lane;
+        if (lane == 0) s_n_local = __popc(bal);
     }
     __syncthreads();
     Segment sg = cta_segment(s_n_local, p.gpg);
@@ -203,7 +209,7 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
 
     if (sg.ng > 0 && warp == 0) {
         // ================= TMA producer: lane j -> B box j, lane 0 also the A box =================
-        const dcmoe_mtile mt = p.mtiles[sg.m];
+        const dcmoe_mtile mt = s_mt[sg.m];
         const CUtensorMap* amap = SWIGLU ? (mt.group == p.n_real ? &tmap_a0 : &tmap_a1) : &tmap_a0;
         const int a_row = SWIGLU ? mt.a_row : mt.out_row;
         // GEMM-1, routed tile, <= 32 token rows: lane j gathers rows 4j .. 4j+3 of the token box from x (one
@@ -359,7 +365,7 @@ ffn_stream_kernel(const __grid_constant__ CUtensorMap tmap_a0,   // GEMM-1: x   
     } else if (sg.ng > 0 && warp >= 4) {
         // ================= epilogue: TMEM lane = output column, TMEM column = token =================
         const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
-        const dcmoe_mtile mt = p.mtiles[sg.m];
+        const dcmoe_mtile mt = s_mt[sg.m];
         const bool shared_grp = mt.group == p.n_real;
         mbar_wait(tfull_bar, 0u);
         tc_fence_after();
