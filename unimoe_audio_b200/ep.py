@@ -10,7 +10,7 @@ rank of the group must call in lockstep with token counts on the same side of th
             call (72 us per layer call, the single-GPU latency).  Policy "exchange" (DCMOE_EP_DECODE=exchange; the same T
             on every rank): the TOKENS are replicated (pushed into every rank's buffer over NVLink), routed identically
             everywhere, each rank streams only ITS experts' weights, and the combine gathers each token's routed rows
-            from their owners' y -- 88 us at 2 GPUs, 104 us at 8 (two cross-GPU barriers per call): at this size the
+            from their owners' y -- 88 us at 2 GPUs, 98 us at 8 (two cross-GPU barriers per call): at this size the
             layer is bound by per-kernel fixed costs, not by the weight bytes a rank streams.
   dispatch  the reference's exchange, un-padded: the permute kernel stores each selected row straight into the owner's
             packed buffer over NVLink (``ep_dispatch``), the owners run the grouped FFN on the rows they received, the
@@ -379,7 +379,7 @@ class ExpertParallelDCMoE:
         # decode-sized calls (world * T <= 64): "replicate" (default) = keep a resident copy of the remote experts' packs
         # (fetched once over NVLink, 270 MB x (R-1)/R per layer) and run the call with no per-call exchange at all;
         # "exchange" = replicate the TOKENS instead (decode_forward); "0" = take the large-T paths.  Measured at 8 GPUs
-        # (profiles/r02_ep_decode_latency.txt): exchange 104 us per layer call against 72-85 us on one GPU -- at this size the
+        # (profiles/r02_ep_decode_latency.txt): exchange 98 - 107 us per layer call against 70 - 82 us on one GPU (and 71 - 79 us for the replica) -- at this size the
         # layer is bound by per-kernel fixed costs, not by the weight bytes a rank streams, so sharding them buys nothing
         env_d = os.environ.get("DCMOE_EP_DECODE", "replicate")
         self.decode_policy = {"1": "exchange", "0": "off"}.get(env_d, env_d)
