@@ -23,84 +23,104 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
+// One CTA, 32 warps.  The token blocks are cut into 32 contiguous chunks, one per warp:
+//   phase 1  every warp sums its chunk per column (lane = block, 32 blocks per round, all loads of a round in flight:
+//            counts as integers, the aux-softmax partials in fp64) -> chunk totals;
+//   phase 2  16 threads prefix the 32 chunk totals per column -> chunk bases, expert counts, aux terms;
+//   phase 3  every warp rescans its chunk (L1 / L2 hits) and writes the exclusive per-block offsets: warp scan across
+//            the 32 blocks of a round + the running carry + the chunk base;
+//   phase 4  segment bases (thread 0) and the tile table (all threads).
+// The former version scanned an expert's blocks with ONE warp, 512 blocks per dependent step: 14 us at 1,024 blocks,
+// 129 us at 8,192, 262 us at 16,384 (serial latency in front of the permute and the GEMMs).
 template <bool BF16>
 __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int n_real, int64_t T, int t_pad,
                                                     int max_mtiles, PlanView pv) {
+    __shared__ int s_chunk_cnt[32][kMaxDyn];
+    __shared__ double s_chunk_prob[32][kMaxDyn];
+    __shared__ int s_chunk_base[32][kMaxDyn];
     __shared__ int s_counts[kMaxDyn];
     __shared__ int s_seg[kMaxDyn + 1];
     __shared__ int s_tile0[kMaxDyn + 1];
     __shared__ double s_term[kMaxDyn];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_warp = (n_blocks + 31) / 32;
+    const int b0 = min(n_blocks, warp * per_warp), b1 = min(n_blocks, b0 + per_warp);
 
-    if (warp < n_real) {
-        // exclusive scan of expert `warp` over token blocks: 16 consecutive blocks per lane, 512 per step
-        const int e = warp;
-        int carry = 0;
-        constexpr int PER = 16;
-        for (int base = 0; base < n_blocks; base += 32 * PER) {
-            int v[PER], sum = 0;
+    {   // ---- phase 1: chunk totals ----
+        int cnt[kMaxDyn];
+        double pr[kMaxDyn];
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int b = base + lane * PER + i;
-                v[i] = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
-            }
+        for (int j = 0; j < kMaxDyn; ++j) { cnt[j] = 0; pr[j] = 0.0; }
+        for (int b = b0 + lane; b < b1; b += 32) {
+            const int32_t* c = pv.block_counts + (int64_t)b * n_dyn;
+            const float* q = pv.block_probs + (int64_t)b * n_dyn;
 #pragma unroll
-            for (int i = 0; i < PER; ++i) sum += v[i];
-            int incl = sum;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                int o = __shfl_up_sync(kFull, incl, off);
-                if (lane >= off) incl += o;
-            }
-            int run = carry + incl - sum;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int b = base + lane * PER + i;
-                if (b < n_blocks) pv.block_offsets[(int64_t)b * n_real + e] = run;
-                run += v[i];
-            }
-            carry += __shfl_sync(kFull, incl, 31);
-        }
-        if (lane == 0) {
-            s_counts[e] = carry;
-            pv.counts[e] = carry;
-        }
-    } else if (warp >= 16 && warp < 16 + n_dyn) {
-        // aux loss (core.py:376-389, aux_balance_weight = None): column means over tokens.  Fixed reduction
-        // shape (lane-strided partial sums, xor tree) -> bit-stable run to run.
-        const int j = warp - 16;
-        double ps = 0.0;
-        long long ts = 0;
-        constexpr int U = 16;                                      // independent loads in flight per lane
-        for (int b0 = lane; b0 < n_blocks; b0 += 32 * U) {
-            float pr[U];
-            int ct[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int b = b0 + 32 * u;
-                pr[u] = b < n_blocks ? pv.block_probs[(int64_t)b * n_dyn + j] : 0.0f;
-                ct[u] = b < n_blocks ? pv.block_counts[(int64_t)b * n_dyn + j] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {                          // fixed order: u ascending
-                ps += (double)pr[u];
-                ts += ct[u];
+            for (int j = 0; j < kMaxDyn; ++j) {
+                if (j < n_dyn) {
+                    cnt[j] += c[j];
+                    pr[j] += (double)q[j];
+                }
             }
         }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            ps += __shfl_xor_sync(kFull, ps, off);
-            ts += __shfl_xor_sync(kFull, ts, off);
-        }
-        if (lane == 0) {
-            float tpe = (float)((double)ts / (double)T);          // torch.mean(expert_mask.float(), 0)
-            float rp = (float)(ps / (double)T);                   // torch.mean(global_weight, 0) ...
-            if (BF16) rp = bf16_round(rp);                        // ... is a D tensor (bf16 rounds here)
-            s_term[j] = (double)(tpe * rp);
+        for (int j = 0; j < kMaxDyn; ++j) {
+            if (j < n_dyn) {                                   // (warp-uniform) fixed xor tree: bit-stable run to run
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    cnt[j] += __shfl_xor_sync(kFull, cnt[j], off);
+                    pr[j] += __shfl_xor_sync(kFull, pr[j], off);
+                }
+                if (lane == 0) {
+                    s_chunk_cnt[warp][j] = cnt[j];
+                    s_chunk_prob[warp][j] = pr[j];
+                }
+            }
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < n_dyn) {   // ---- phase 2: chunk bases, totals, aux terms (core.py:376-389, aux_balance_weight = None) ----
+        const int j = threadIdx.x;
+        int base = 0;
+        double ps = 0.0;
+        for (int w = 0; w < 32; ++w) {                         // fixed order over the chunks
+            s_chunk_base[w][j] = base;
+            base += s_chunk_cnt[w][j];
+            ps += s_chunk_prob[w][j];
+        }
+        s_counts[j] = base;
+        if (j < n_real) pv.counts[j] = base;
+        float tpe = (float)((double)base / (double)T);         // torch.mean(expert_mask.float(), 0)
+        float rp = (float)(ps / (double)T);                    // torch.mean(global_weight, 0) ...
+        if (BF16) rp = bf16_round(rp);                         // ... is a D tensor (bf16 rounds here)
+        s_term[j] = (double)(tpe * rp);
+    }
+    __syncthreads();
+    {   // ---- phase 3: exclusive per-block offsets of the routed experts ----
+        int carry[kMaxDyn];
+#pragma unroll
+        for (int e = 0; e < kMaxDyn; ++e) carry[e] = e < n_real ? s_chunk_base[warp][e] : 0;
+        for (int bb = b0; bb < b1; bb += 32) {
+            const int b = bb + lane;
+            const bool ok = b < b1;
+            int c[kMaxDyn];
+#pragma unroll
+            for (int e = 0; e < kMaxDyn; ++e) c[e] = (ok && e < n_real) ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
+#pragma unroll
+            for (int e = 0; e < kMaxDyn; ++e) {
+                if (e < n_real) {                              // warp-uniform
+                    int incl = c[e];
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int o = __shfl_up_sync(kFull, incl, off);
+                        if (lane >= off) incl += o;
+                    }
+                    if (ok) pv.block_offsets[(int64_t)b * n_real + e] = carry[e] + incl - c[e];
+                    carry[e] += __shfl_sync(kFull, incl, 31);
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {   // ---- phase 4 ----
         int row = t_pad;
         int tile = t_pad / kTileM;
         for (int e = 0; e < n_real; ++e) {
