@@ -595,6 +595,18 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "peaks": peaks,
         }
+        if workload_id == "c4" and world > 1:
+            # the same workload on ONE GPU (`--gpus 1 --workload c4`, a separate run: it cannot be timed inside a multi-rank
+            # job), so that the line carries its own same-workload scaling reference next to the driver's N = 1 line
+            ref_path = os.path.join(ROOT, "profiles", "r02_bench_n1_configs3_steps10.json")
+            try:
+                with open(ref_path) as fh:
+                    ref1 = json.loads([ln for ln in fh if ln.startswith("{")][0])
+                line["same_workload_n1"] = {"value": ref1["value"], "ms_per_step": ref1["ms_per_step"], "sm_mhz": ref1["clocks"]["sm_mhz"],
+                                            "source": "profiles/r02_bench_n1_configs3_steps10.json (committed earlier run, not this job)",
+                                            "efficiency_vs_it": value / (world * ref1["value"])}
+            except Exception:  # noqa: BLE001
+                pass
         print(json.dumps(line), flush=True)
     ok = bool(parity.get("ok", False))
     if world > 1:
