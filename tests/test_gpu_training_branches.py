@@ -125,6 +125,23 @@ def test_token_drop_full_layer_matches_oracle(dev):
     np.testing.assert_allclose(out[5].item(), ref.aux_loss.item(), rtol=2e-3)
 
 
+def test_token_drop_with_zero_capacity_drops_every_routed_expert(dev):
+    """capacity_factor = 0, min_capacity = 0 -> torch.topk(k = 0): every routed column is cleared, the layer is the two
+    shared experts weighted by their 2-way softmax (core.py:306-316, :188-192)."""
+    dt = torch.bfloat16
+    cfg = dict(token_drop=True, drop_policy="probs", capacity_factor=0.0, min_capacity=0)
+    m, W = _module(dt, dev, **cfg)
+    x = torch.randn(1, 100, 2048, generator=torch.Generator().manual_seed(8)).to(dt)
+    out = m(x.to(dev), None, None)
+    torch.cuda.synchronize()
+    assert int(out[3][:, :9].sum()) == 0 and bool((out[3][:, 9:] == 1).all())
+    assert bool((out[4][:, :9] == 0).all())
+    ref = O.forward(x, W, None, cfg, logits=out[1].cpu())
+    assert torch.equal(out[3].cpu(), ref.expert_mask) and torch.equal(out[4].cpu(), ref.global_weight)
+    a, b = out[0].float().cpu().reshape(-1, 2048), ref.final_hidden_states.float().reshape(-1, 2048)
+    assert ((a - b).abs() <= 1e-2 * b.abs() + 1e-2 * b.abs().max()).all()
+
+
 def test_token_drop_policy_errors(dev):
     from unimoe_audio_b200 import DCMoE
     with pytest.raises(NotImplementedError):

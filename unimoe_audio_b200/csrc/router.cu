@@ -1073,7 +1073,9 @@ __global__ void __launch_bounds__(1024) drop_select_kernel(const void* __restric
     __syncthreads();
     const unsigned n = s_n;
     unsigned long long threshold = 0ull;                  // keep every selected token
-    if ((long long)n > capacity) {
+    if (capacity <= 0) {
+        threshold = ~0ull;                                // torch.topk(k = 0): nothing survives (no key reaches all ones)
+    } else if ((long long)n > capacity) {
         if (tid == 0) { s_prefix = 0ull; s_k = (unsigned long long)capacity; }
         for (int pass = 7; pass >= 0; --pass) {
             if (tid < 256) hist[tid] = 0u;
