@@ -284,7 +284,9 @@ def aux_weighted(logits: torch.Tensor, expert_mask: torch.Tensor, aux_balance_we
     n = (max(T, 1) + _lib.ROUTER_BLOCK - 1) // _lib.ROUTER_BLOCK * 32
     if scratch is None or scratch.numel() < n:
         scratch = ws._aux_scratch = torch.empty(n, dtype=torch.float32, device=logits.device)
-    aux = torch.empty((), dtype=torch.float32, device=logits.device)
+    # (no tokens: the reference's means over an empty dimension are 0 / 0)
+    aux = torch.full((), float("nan"), dtype=torch.float32, device=logits.device) if T == 0 else \
+        torch.empty((), dtype=torch.float32, device=logits.device)
     _lib.check(lib.dcmoe_aux_weighted(_ptr(logits), _TORCH_DT[logits.dtype], _ptr(expert_mask), _ptr(w), 1 if integer else 0,
                                       T, ws.cfg, _ptr(scratch), _ptr(aux), _stream()), "dcmoe_aux_weighted")
     return aux
