@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdcmoe_b200.so")
 SOURCES = ["api.cu", "router.cu", "plan_permute_combine.cu", "ffn_simt.cu", "ffn_tcgen05.cu", "ffn_tcgen05_stream.cu", "rmsnorm.cu", "ep.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "exp_fast.cuh"), os.path.join(HERE, "..", "include", "dcmoe_b200.h")]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "exp_fast.cuh"), os.path.join(CSRC, "route_token.cuh"), os.path.join(HERE, "..", "include", "dcmoe_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

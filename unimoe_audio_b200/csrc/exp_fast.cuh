@@ -23,7 +23,7 @@
 
 namespace dcmoe {
 
-__device__ const float2 kExpTab32[32] = {   // 2^(i/32) = .x + .y
+static __device__ const float2 kExpTab32[32] = {   // 2^(i/32) = .x + .y
     {0x1.000000p+0f, 0x0.0p+0f}, {0x1.059b0ep+0f, -0x1.9d4f52p-25f}, {0x1.0b5586p+0f, 0x1.9f3122p-25f}, {0x1.11301ep+0f, -0x1.fdb496p-25f},
     {0x1.172b84p+0f, -0x1.c15742p-27f}, {0x1.1d4874p+0f, -0x1.d2e8cap-25f}, {0x1.2387a6p+0f, 0x1.ceac48p-25f}, {0x1.29e9e0p+0f, -0x1.5c0424p-25f},
     {0x1.306fe0p+0f, 0x1.4636e2p-25f}, {0x1.371a74p+0f, -0x1.18aac6p-25f}, {0x1.3dea64p+0f, 0x1.824684p-25f}, {0x1.44e086p+0f, 0x1.8624b4p-30f},
@@ -34,9 +34,9 @@ __device__ const float2 kExpTab32[32] = {   // 2^(i/32) = .x + .y
     {0x1.d5818ep+0f, -0x1.822dbcp-27f}, {0x1.dfc974p+0f, -0x1.908c94p-25f}, {0x1.ea4afap+0f, 0x1.52486cp-27f}, {0x1.f50766p+0f, -0x1.246eb0p-26f}};
 
 // the previous definition, kept as the rare path (and for |x| >= 80, NaN, x > 0)
-__device__ __noinline__ float exp_cr_double(float x) { return (float)exp((double)x); }
+static __device__ __noinline__ float exp_cr_double(float x) { return (float)exp((double)x); }
 
-__device__ __forceinline__ float exp_cr(float x) {
+static __device__ __forceinline__ float exp_cr(float x) {
     if (x == 0.0f) return 1.0f;
     if (x > -80.0f && x < 0.0f) {
         const float nf = rintf(__fmul_rn(x, 0x1.715476p+5f));                 // 32 / ln 2
