@@ -142,6 +142,19 @@ def test_token_drop_with_zero_capacity_drops_every_routed_expert(dev):
     assert ((a - b).abs() <= 1e-2 * b.abs() + 1e-2 * b.abs().max()).all()
 
 
+def test_token_drop_prints_the_reference_message_when_asked(dev, capsys):
+    """drop_token_num_print (core.py:316-319): "drop N tokens from total M tokens", N and M counted over the 9 dynamic columns."""
+    dt = torch.bfloat16
+    cfg = dict(token_drop=True, drop_policy="probs", capacity_factor=1.0, min_capacity=8, drop_token_num_print=True)
+    m, W = _module(dt, dev, **cfg)
+    x = torch.randn(1, 512, 2048, generator=torch.Generator().manual_seed(9)).to(dt)
+    out = m(x.to(dev), None, None)
+    torch.cuda.synchronize()
+    pre = R.route(out[1].cpu())[1][:, :9].sum().item()
+    post = out[3][:, :9].sum().item()
+    assert f"drop {pre - post} tokens from total {pre} tokens" in capsys.readouterr().out
+
+
 def test_token_drop_policy_errors(dev):
     from unimoe_audio_b200 import DCMoE
     with pytest.raises(NotImplementedError):
