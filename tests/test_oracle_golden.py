@@ -261,3 +261,37 @@ def test_fp32_gate_training_forward_oracle_matches_reference_golden(golden_dir):
     final = out.final_hidden_states.float().reshape(256, 2048)
     scale = float(np.abs(g["final_rows"]).max())
     np.testing.assert_allclose(final[::2].numpy(), g["final_rows"], rtol=1e-2, atol=1e-2 * scale)
+
+
+# ------------------------------------------------------------------ the router's float-pair exponential (oracle/exp_fast.h)
+def test_exp_fast_statement_is_correctly_rounded_on_a_strided_sweep(tmp_path):
+    """tools/verify_exp_fast.c over every 1024th float of (-80, 0) (the full sweep, 1.1e9 inputs, is recorded in
+    profiles/r02_exp_fast_exhaustive.txt): no accepted value may differ from the long-double exponential, and the previous
+    definition (float)exp((double)x) must agree with it everywhere."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "verify_exp_fast")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", exe, os.path.join(root, "tools", "verify_exp_fast.c"), "-lm"], check=True)
+    res = subprocess.run([exe, "1024"], capture_output=True, text=True, check=True)
+    m = re.search(r"inputs (\d+)\s+accepted-but-wrong (\d+)\s+fallbacks (\d+).*correctly rounded: (\d+)", res.stdout)
+    assert m, res.stdout
+    n, wrong, fb, dbl = (int(v) for v in m.groups())
+    assert n > 1_000_000 and wrong == 0 and dbl == 0 and fb < n // 10_000
+
+
+def test_exp_fast_agrees_with_the_double_precision_definition():
+    import ctypes
+    lib = R.lib()
+    rng = np.random.default_rng(5)
+    a = (rng.standard_normal(20000) * 1.5).astype(np.float32)
+    b = (rng.standard_normal(20000) * 1.5).astype(np.float32)
+    xs = -np.abs(torch.from_numpy(a).to(torch.bfloat16).float().numpy() - torch.from_numpy(b).to(torch.bfloat16).float().numpy())
+    fb = ctypes.c_int(0)
+    n_fb = 0
+    for x in xs.tolist() + [0.0, -1e-30, -79.9, -80.0, -100.0]:
+        v = lib.dcmoe_oracle_exp_fast(x, ctypes.byref(fb))
+        n_fb += fb.value
+        if not fb.value:
+            assert np.float32(v).tobytes() == np.float32(lib.dcmoe_oracle_exp_cr(x)).tobytes(), x
+    assert n_fb <= 5
