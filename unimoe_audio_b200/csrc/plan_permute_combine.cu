@@ -23,47 +23,62 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------
-// One CTA, 32 warps.  The token blocks are cut into 32 contiguous chunks, one per warp:
+// One CTA, 16 warps.  The token blocks are cut into 16 contiguous chunks, one per warp:
 //   phase 1  every warp sums its chunk per column (lane = block, 32 blocks per round, all loads of a round in flight:
 //            counts as integers, the aux-softmax partials in fp64) -> chunk totals;
-//   phase 2  16 threads prefix the 32 chunk totals per column -> chunk bases, expert counts, aux terms;
+//   phase 2  16 threads prefix the 16 chunk totals per column -> chunk bases, expert counts, aux terms;
 //   phase 3  every warp rescans its chunk (L1 / L2 hits) and writes the exclusive per-block offsets: warp scan across
 //            the 32 blocks of a round + the running carry + the chunk base;
 //   phase 4  segment bases (thread 0) and the tile table (all threads).
 // The former version scanned an expert's blocks with ONE warp, 512 blocks per dependent step: 14 us at 1,024 blocks,
 // 129 us at 8,192, 262 us at 16,384 (serial latency in front of the permute and the GEMMs).
-template <bool BF16>
-__global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int n_real, int64_t T, int t_pad,
-                                                    int max_mtiles, PlanView pv) {
-    __shared__ int s_chunk_cnt[32][kMaxDyn];
-    __shared__ double s_chunk_prob[32][kMaxDyn];
-    __shared__ int s_chunk_base[32][kMaxDyn];
+// (kPlanWarps warps; CN = compile-time column bound: 9 for the reference's expert counts, where four rounds of loads
+// -- 4 x 18 values per lane -- are in flight at once, else kMaxDyn with one round)
+constexpr int kPlanWarps = 16;
+template <bool BF16, int CN>
+__global__ void __launch_bounds__(kPlanWarps * 32) plan_kernel(int n_blocks, int n_dyn, int n_real, int64_t T, int t_pad,
+                                                                int max_mtiles, PlanView pv) {
+    constexpr int U = CN <= 9 ? 4 : 1;             // rounds of 32 blocks whose loads are issued together
+    __shared__ int s_chunk_cnt[kPlanWarps][kMaxDyn];
+    __shared__ double s_chunk_prob[kPlanWarps][kMaxDyn];
+    __shared__ int s_chunk_base[kPlanWarps][kMaxDyn];
     __shared__ int s_counts[kMaxDyn];
     __shared__ int s_seg[kMaxDyn + 1];
     __shared__ int s_tile0[kMaxDyn + 1];
     __shared__ double s_term[kMaxDyn];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per_warp = (n_blocks + 31) / 32;
+    const int per_warp = (n_blocks + kPlanWarps - 1) / kPlanWarps;
     const int b0 = min(n_blocks, warp * per_warp), b1 = min(n_blocks, b0 + per_warp);
 
     {   // ---- phase 1: chunk totals ----
-        int cnt[kMaxDyn];
-        double pr[kMaxDyn];
+        int cnt[CN];
+        double pr[CN];
 #pragma unroll
-        for (int j = 0; j < kMaxDyn; ++j) { cnt[j] = 0; pr[j] = 0.0; }
-        for (int b = b0 + lane; b < b1; b += 32) {
-            const int32_t* c = pv.block_counts + (int64_t)b * n_dyn;
-            const float* q = pv.block_probs + (int64_t)b * n_dyn;
+        for (int j = 0; j < CN; ++j) { cnt[j] = 0; pr[j] = 0.0; }
+        for (int bb = b0 + lane; bb < b1; bb += 32 * U) {
+            int c[U][CN];
+            float q[U][CN];
 #pragma unroll
-            for (int j = 0; j < kMaxDyn; ++j) {
-                if (j < n_dyn) {
-                    cnt[j] += c[j];
-                    pr[j] += (double)q[j];
+            for (int u = 0; u < U; ++u) {
+                const int b = bb + 32 * u;
+#pragma unroll
+                for (int j = 0; j < CN; ++j) {
+                    const bool ok = b < b1 && j < n_dyn;
+                    c[u][j] = ok ? pv.block_counts[(int64_t)b * n_dyn + j] : 0;
+                    q[u][j] = ok ? pv.block_probs[(int64_t)b * n_dyn + j] : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int j = 0; j < CN; ++j) {
+                    cnt[j] += c[u][j];
+                    pr[j] += (double)q[u][j];
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < kMaxDyn; ++j) {
+        for (int j = 0; j < CN; ++j) {
             if (j < n_dyn) {                                   // (warp-uniform) fixed xor tree: bit-stable run to run
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
@@ -82,7 +97,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
         const int j = threadIdx.x;
         int base = 0;
         double ps = 0.0;
-        for (int w = 0; w < 32; ++w) {                         // fixed order over the chunks
+        for (int w = 0; w < kPlanWarps; ++w) {                 // fixed order over the chunks
             s_chunk_base[w][j] = base;
             base += s_chunk_cnt[w][j];
             ps += s_chunk_prob[w][j];
@@ -96,26 +111,33 @@ __global__ void __launch_bounds__(1024) plan_kernel(int n_blocks, int n_dyn, int
     }
     __syncthreads();
     {   // ---- phase 3: exclusive per-block offsets of the routed experts ----
-        int carry[kMaxDyn];
+        int carry[CN];
 #pragma unroll
-        for (int e = 0; e < kMaxDyn; ++e) carry[e] = e < n_real ? s_chunk_base[warp][e] : 0;
-        for (int bb = b0; bb < b1; bb += 32) {
-            const int b = bb + lane;
-            const bool ok = b < b1;
-            int c[kMaxDyn];
+        for (int e = 0; e < CN; ++e) carry[e] = e < n_real ? s_chunk_base[warp][e] : 0;
+        for (int bb = b0; bb < b1; bb += 32 * U) {
+            int c[U][CN];
 #pragma unroll
-            for (int e = 0; e < kMaxDyn; ++e) c[e] = (ok && e < n_real) ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
+            for (int u = 0; u < U; ++u) {
+                const int b = bb + 32 * u + lane;
 #pragma unroll
-            for (int e = 0; e < kMaxDyn; ++e) {
-                if (e < n_real) {                              // warp-uniform
-                    int incl = c[e];
+                for (int e = 0; e < CN; ++e) c[u][e] = (b < b1 && e < n_real) ? pv.block_counts[(int64_t)b * n_dyn + e] : 0;
+            }
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int o = __shfl_up_sync(kFull, incl, off);
-                        if (lane >= off) incl += o;
+            for (int u = 0; u < U; ++u) {
+                const int b = bb + 32 * u + lane;
+                if (bb + 32 * u >= b1) break;                  // (warp-uniform)
+#pragma unroll
+                for (int e = 0; e < CN; ++e) {
+                    if (e < n_real) {                          // warp-uniform
+                        int incl = c[u][e];
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const int o = __shfl_up_sync(kFull, incl, off);
+                            if (lane >= off) incl += o;
+                        }
+                        if (b < b1) pv.block_offsets[(int64_t)b * n_real + e] = carry[e] + incl - c[u][e];
+                        carry[e] += __shfl_sync(kFull, incl, 31);
                     }
-                    if (ok) pv.block_offsets[(int64_t)b * n_real + e] = carry[e] + incl - c[e];
-                    carry[e] += __shfl_sync(kFull, incl, 31);
                 }
             }
         }
@@ -285,10 +307,12 @@ __global__ void pack_kernel(const char* __restrict__ gate_proj, const char* __re
 
 int launch_plan(int64_t T, const dcmoe_config* cfg, const dcmoe_sizes& sz, PlanView pv, cudaStream_t stream) {
     const int n_dyn = cfg->n_real + cfg->n_null;
-    if (cfg->dtype == DCMOE_BF16)
-        plan_kernel<true><<<1, 1024, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv);
-    else
-        plan_kernel<false><<<1, 1024, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv);
+#define DCMOE_LAUNCH_PLAN(BF, CN_) \
+    plan_kernel<BF, CN_><<<1, kPlanWarps * 32, 0, stream>>>((int)sz.n_blocks, n_dyn, cfg->n_real, T, (int)sz.t_pad, (int)sz.max_mtiles, pv)
+    const bool bf = cfg->dtype == DCMOE_BF16;
+    if (n_dyn <= 9) { if (bf) DCMOE_LAUNCH_PLAN(true, 9); else DCMOE_LAUNCH_PLAN(false, 9); }
+    else { if (bf) DCMOE_LAUNCH_PLAN(true, kMaxDyn); else DCMOE_LAUNCH_PLAN(false, kMaxDyn); }
+#undef DCMOE_LAUNCH_PLAN
     return check_cuda(cudaGetLastError(), "plan_kernel launch");
 }
 
